@@ -1,0 +1,118 @@
+/* include/minife_b200.h -- C ABI of libminife_b200.so, the B200-native (sm_100a) implementation of the
+ * miniFE hot path: hex8 FE assembly + unpreconditioned CG.  Plain pointers and sizes only.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the Mantevo/miniFE tree).
+ * One mfe_ctx == one MPI rank of the reference == one GPU.  Device state (CSR arrays, vectors, halo
+ * buffers) lives in the context; host arrays are only touched by the *_export / *_import calls and by
+ * the host-buffer arguments documented below.  All functions return 0 on success, nonzero on error
+ * (message via mfe_last_error()).  Every phase call returns after its stream is synchronised, so host
+ * wall clocks around a call (ref/src/driver.hpp:74-88 RUN_TIMED_FUNCTION) are honest.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with an error.
+ */
+#ifndef MINIFE_B200_H
+#define MINIFE_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mfe_ctx mfe_ctx;
+
+#define MFE_ABI_VERSION 1
+
+/* cg_times[] slots, same order as ref/utils/mytimer.hpp:37-44 */
+enum { MFE_WAXPY = 0, MFE_DOT = 1, MFE_MATVEC = 2, MFE_MATVECDOT = 3, MFE_TOTAL = 4, MFE_NUM_TIMERS = 5 };
+
+/* dot-product algorithm (ref/src/Vector_functions.hpp:194-226 sums strictly left to right):
+ *   MFE_DOT_EXACT   parallel order-reproducing sum: bit-identical to the serial loop (default)
+ *   MFE_DOT_SERIAL  one device thread, the literal loop (validation of MFE_DOT_EXACT; slow)
+ *   MFE_DOT_TREE    conventional warp/block tree (NOT reproducible vs the reference; comparison only) */
+enum { MFE_DOT_EXACT = 0, MFE_DOT_SERIAL = 1, MFE_DOT_TREE = 2 };
+
+int         mfe_abi_version(void);
+const char *mfe_last_error(void);
+int         mfe_device_count(void);
+
+/* ref/utils/BoxPartition.cpp:79-122 as called at ref/src/main.cpp:112: box_partition(0,np,2,global,boxes).
+ * boxes6n[6*p+{0..5}] = {x0,x1,y0,y1,z0,z1} element ranges of rank p.  Host only. */
+int mfe_box_partition(int nx, int ny, int nz, int nranks, int *boxes6n);
+
+/* Context for `rank` of `nranks` on CUDA device `device`.  global_box / all_boxes as produced by
+ * mfe_box_partition (ref/src/main.cpp:100-114).  Replaces simple_mesh_description's ctor
+ * (ref/src/simple_mesh_description.hpp:41-226): id->row map and BC sets become analytic functions of the
+ * box table. */
+mfe_ctx *mfe_create(int rank, int nranks, int device, const int global_box[6], const int *all_boxes6n);
+void     mfe_destroy(mfe_ctx *ctx);
+
+/* multi-GPU plumbing (replaces MPI_Init/MPI_COMM_WORLD): rank 0 calls mfe_comm_unique_id, the id is
+ * distributed by the launcher (torch.distributed / file / MPI), every rank calls mfe_comm_init. */
+int mfe_comm_unique_id(char id128[128]);
+int mfe_comm_init(mfe_ctx *ctx, const char id128[128]);
+
+/* ref/src/generate_matrix_structure.hpp:47-149 (+ MatrixInitOp.hpp:127-156, SparseMatrix_functions.hpp:56-74) */
+int mfe_generate_matrix_structure(mfe_ctx *ctx, int64_t *nrows, int64_t *first_row, int64_t *nnz);
+/* ref/src/assemble_FE_data.hpp:38-73 -> perform_element_loop.hpp:40-104 -> sum_into_global_linear_system
+ * (SparseMatrix_functions.hpp:245-255).  b is zero-initialised by generate_matrix_structure (Vector.hpp:44-52). */
+int mfe_assemble_FE_data(mfe_ctx *ctx);
+/* ref/src/SparseMatrix_functions.hpp:431-480 impose_dirichlet(prescribed_value, A, b, ..., bc_rows):
+ * which_set 0 = mesh.bc_rows_0 (faces x=0,y=0,z=0,y=1,z=1), 1 = mesh.bc_rows_1 (face x=1)
+ * (ref/src/driver.hpp:215-218).  Must precede mfe_make_local_matrix (columns are still global rows). */
+int mfe_impose_dirichlet(mfe_ctx *ctx, double prescribed_value, int which_set);
+/* ref/src/make_local_matrix.hpp:42-442 */
+int mfe_make_local_matrix(mfe_ctx *ctx, int64_t *num_cols);
+
+/* ref/src/cg_solve.hpp:69-229 with matvec_std (SparseMatrix_functions.hpp:546-578).
+ * x_host: in = initial guess, out = solution (nrows doubles; NULL: use/keep the device-resident x).
+ * normr_hist (NULL or max_iter+1 doubles): hist[0] = initial residual norm, hist[k] = the norm the reference
+ * would print for iteration k.  Returns 0, or 1 on numerical breakdown (cg_solve.hpp:186-198). */
+int mfe_cg_solve(mfe_ctx *ctx, double *x_host, int max_iter, double tolerance, int *num_iters, double *normr,
+                 double cg_times[MFE_NUM_TIMERS], double *normr_hist, double *rtrans_hist, double *pap_hist,
+                 double *alpha_hist);
+int mfe_set_dot_mode(mfe_ctx *ctx, int mode);
+/* 1: record per-op-class CUDA events to fill cg_times[WAXPY,DOT,MATVEC] (default), 0: only TOTAL */
+int mfe_set_op_timing(mfe_ctx *ctx, int enabled);
+
+/* kernel-level entry points on HOST buffers (H2D + kernel + D2H inside the call) -- used by parity tests and
+ * by the reference-side shims of matvec_std / waxpby / dot.
+ * mfe_matvec: ref matvec_std::operator() incl. exchange_externals; x has num_cols entries (externals are
+ * overwritten by the halo exchange when nranks > 1), y has nrows. */
+int mfe_matvec(mfe_ctx *ctx, double *x_host, double *y_host);
+int mfe_waxpby(mfe_ctx *ctx, int64_t n, double alpha, const double *x_host, double beta, const double *y_host, double *w_host); /* Vector_functions.hpp:127-150 */
+int mfe_dot(mfe_ctx *ctx, int64_t n, const double *x_host, const double *y_host, double *result); /* Vector_functions.hpp:194-226 (local part + rank-ordered sum) */
+/* ref/src/exchange_externals.hpp:44-161 on a host vector of num_cols entries */
+int mfe_exchange_externals(mfe_ctx *ctx, double *x_host);
+
+/* sizes */
+int64_t mfe_nrows(const mfe_ctx *ctx);
+int64_t mfe_first_row(const mfe_ctx *ctx);
+int64_t mfe_nnz(const mfe_ctx *ctx);
+int64_t mfe_num_cols(const mfe_ctx *ctx);
+/* name in {external_index, external_local_index, elements_to_send, neighbors, recv_length, send_length}
+ * (ref/src/CSRMatrix.hpp:73-78); returns count (or -1), fills out[] when non-NULL */
+int64_t mfe_get_map(const mfe_ctx *ctx, const char *name, int *out);
+
+/* copy device state into caller-owned host buffers (any pointer may be NULL = skip).
+ * rows[nrows], row_offsets[nrows+1] (int32 as CSRMatrix.hpp:64-66; fails if nnz > INT32_MAX, use
+ * row_offsets64), packed_cols[nnz], packed_coefs[nnz] */
+int mfe_export_csr(mfe_ctx *ctx, int *rows, int *row_offsets, int64_t *row_offsets64, int *packed_cols, double *packed_coefs);
+int mfe_export_vector(mfe_ctx *ctx, const char *name /* "b" | "x" */, double *out);
+int mfe_import_vector(mfe_ctx *ctx, const char *name /* "b" | "x" */, const double *in);
+/* replace the device CSR by caller arrays already in local-index form (ref/basic utest pll_matvec style
+ * hand matrices; also the shim path for a CSRMatrix assembled elsewhere).  int32 offsets. */
+int mfe_import_csr(mfe_ctx *ctx, int64_t nrows, int64_t num_cols, const int *row_offsets, const int *packed_cols, const double *packed_coefs);
+
+/* timed repetitions of single kernels on device-resident data, for bench.py / ncu: returns the average
+ * milliseconds per launch over `reps` launches (CUDA events on the launching stream).
+ * what: "matvec", "matvec_dot", "waxpby", "dot_rr", "dot_pap", "xr_update", "cg_iteration" */
+int mfe_time_kernel(mfe_ctx *ctx, const char *what, int reps, double *ms_per_launch);
+/* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
+int64_t mfe_launch_count(const mfe_ctx *ctx);
+/* phase timings of the last calls, milliseconds: "structure","assembly","assembly_elem","assembly_gather",
+ * "dirichlet0","dirichlet1","make_local","cg" */
+double mfe_phase_ms(const mfe_ctx *ctx, const char *phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

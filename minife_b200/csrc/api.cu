@@ -1,0 +1,959 @@
+// api.cu -- context, host-side orchestration and the extern "C" surface declared in include/minife_b200.h.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/minife_b200.h"
+#include "kernels.cuh"
+#include "halo_maps.h"
+
+using namespace mfe;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e_ = (call);                                                                         \
+    if (e_ != cudaSuccess) return fail("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define CKN(call)                                                                                    \
+  do {                                                                                               \
+    int r_ = (call);                                                                                 \
+    if (r_ != 0) return fail("%s:%d %s: NCCL error %d (%s)", __FILE__, __LINE__, #call, r_, nccl_errstr(r_)); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, bound lazily (dlopen) so that the library loads on a box without NCCL / without a GPU
+// ---------------------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_t_;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+  int (*CommInitRank)(ncclComm_t_ *, int, ncclUniqueId_t, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t_) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Send)(const void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+  int (*Recv)(void *, size_t, int, int, ncclComm_t_, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, ncclComm_t_, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+enum { NCCL_FLOAT64 = 8, NCCL_INT32 = 2 };   // ncclDataType_t values (nccl.h)
+static const char *nccl_errstr(int r) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"; }
+static int nccl_load()
+{
+  if (g_nccl.h) return 0;
+  const char *names[] = { "libnccl.so.2", "libnccl.so" };
+  for (const char *n : names) { g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.h) break; }
+  if (!g_nccl.h) return fail("cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                  \
+  *(void **)(&g_nccl.field) = dlsym(g_nccl.h, name);                                      \
+  if (!g_nccl.field) return fail("libnccl: missing symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
+  SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
+  SYM(AllGather, "ncclAllGather") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------------------
+enum { MV_TR = 64 };            // rows per SpMV tile (must divide DOT_CHUNK)
+
+struct DotWs {                  // workspace of one exact dot (sized for nrows)
+  DotWork w{};
+  double *chunk_tmp = nullptr;
+};
+
+struct mfe_ctx {
+  int rank = 0, nranks = 1, device = 0;
+  MeshDesc m{};
+  std::vector<RankBox> boxes;
+  RankBox *d_boxes = nullptr;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+
+  // CSR (device)
+  int64_t nrows = 0, nnz = 0, nnz_padded = 0, num_cols = 0;
+  int *d_rows = nullptr;
+  uint32_t *d_roff = nullptr;
+  int *d_cols = nullptr;
+  double *d_coefs = nullptr;
+  int64_t ntiles = 0;
+  int64_t *d_tile_base = nullptr;
+  bool has_structure = false, has_local = false, mesh_csr = true;
+
+  // vectors (device)
+  double *d_b = nullptr, *d_x = nullptr, *d_r = nullptr, *d_p = nullptr, *d_Ap = nullptr;
+  double *d_tmp1 = nullptr, *d_tmp2 = nullptr;        // scratch for the host-buffer entry points
+  int64_t vec_cap = 0;
+
+  // index maps (host, as the reference's CSRMatrix fields) + device copies used by the halo exchange
+  std::vector<int> external_index, external_local_index, elements_to_send, neighbors, recv_length, send_length;
+  int *d_elements_to_send = nullptr;
+  double *d_send_buf = nullptr;
+
+  // CG state
+  CgScalars *d_sc = nullptr;
+  double *d_hist = nullptr;      // 4 * (max_iter+1)
+  int hist_cap = 0;
+  double *d_tile_sums = nullptr; // ntiles
+  DotWs dot;
+  double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
+  int dot_mode = MFE_DOT_EXACT;
+  int op_timing = 1;
+
+  // comm
+  ncclComm_t_ comm = nullptr;
+
+  // phase timings (ms)
+  double t_structure = 0, t_assembly = 0, t_assembly_elem = 0, t_assembly_gather = 0, t_dir0 = 0, t_dir1 = 0, t_make_local = 0, t_cg = 0;
+};
+
+static int free_dev(void *p) { if (p) cudaFree(p); return 0; }
+
+template <typename T>
+static int dev_alloc(T **p, int64_t n)
+{
+  *p = nullptr;
+  cudaError_t e = cudaMalloc((void **)p, (size_t)std::max<int64_t>(n, 1) * sizeof(T));
+  if (e != cudaSuccess) return fail("cudaMalloc(%lld bytes): %s", (long long)(n * (int64_t)sizeof(T)), cudaGetErrorString(e));
+  return 0;
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+
+// ---------------------------------------------------------------------------------------------------------
+// box_partition: ref/utils/BoxPartition.cpp:79-122 (recursive coordinate bisection, z then y then x)
+// ---------------------------------------------------------------------------------------------------------
+static void rcb(int ip, int up, int axis, const int *box, int *out)
+{
+  const int np = up - ip;
+  if (np == 1) { for (int i = 0; i < 6; ++i) out[6 * ip + i] = box[i]; return; }
+  const int n = box[2 * axis + 1] - box[2 * axis];
+  const int np_low = np / 2, np_upp = np - np_low;
+  const int n_upp = (int)(((double)n) * (((double)np_upp) / ((double)np)));
+  const int n_low = n - n_upp;
+  const int next = (axis + 2) % 3;
+  int lowb[6], uppb[6];
+  for (int i = 0; i < 6; ++i) lowb[i] = uppb[i] = box[i];
+  lowb[2 * axis + 1] = box[2 * axis] + n_low;
+  uppb[2 * axis] = box[2 * axis] + n_low;
+  uppb[2 * axis + 1] = uppb[2 * axis] + n_upp;
+  if (np_low) rcb(ip, ip + np_low, next, lowb, out);
+  rcb(ip + np_low, up, next, uppb, out);
+}
+
+extern "C" int mfe_abi_version(void) { return MFE_ABI_VERSION; }
+extern "C" const char *mfe_last_error(void) { return g_err.c_str(); }
+extern "C" int mfe_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+extern "C" int mfe_box_partition(int nx, int ny, int nz, int nranks, int *boxes)
+{
+  if (nx < 1 || ny < 1 || nz < 1 || nranks < 1 || !boxes) return fail("mfe_box_partition: bad arguments");
+  const int g[6] = { 0, nx, 0, ny, 0, nz };
+  rcb(0, nranks, 2, g, boxes);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------------------------------
+static void fill_mesh(mfe_ctx *c, const int gb[6], const int *all)
+{
+  MeshDesc &m = c->m;
+  m.nx = gb[1]; m.ny = gb[3]; m.nz = gb[5];
+  m.gnx = m.nx + 1; m.gny = m.ny + 1; m.gnz = m.nz + 1;
+  m.nranks = c->nranks; m.rank = c->rank;
+  const int g[3] = { m.nx, m.ny, m.nz };
+  c->boxes.resize(c->nranks);
+  int off = 0;
+  for (int p = 0; p < c->nranks; ++p) {
+    RankBox &b = c->boxes[p];
+    const int *eb = all + 6 * p;
+    for (int a = 0; a < 3; ++a) {      // simple_mesh_description.hpp:49-53
+      b.nb[2 * a] = eb[2 * a];
+      b.nb[2 * a + 1] = eb[2 * a + 1] + ((eb[2 * a + 1] > eb[2 * a] && eb[2 * a + 1] == g[a]) ? 1 : 0);
+    }
+    b.nrows = (b.nb[1] - b.nb[0]) * (b.nb[3] - b.nb[2]) * (b.nb[5] - b.nb[4]);
+    b.first_row = off;                 // box_utils.hpp:254-264
+    off += b.nrows;
+  }
+  const int *eb = all + 6 * c->rank;
+  for (int i = 0; i < 6; ++i) { m.eb[i] = eb[i]; m.nb[i] = c->boxes[c->rank].nb[i]; }
+  m.lnx = m.nb[1] - m.nb[0]; m.lny = m.nb[3] - m.nb[2]; m.lnz = m.nb[5] - m.nb[4];
+  m.first_row = c->boxes[c->rank].first_row;
+  m.nrows = c->boxes[c->rank].nrows;
+  for (int a = 0; a < 3; ++a) { m.face_lo[a] = eb[2 * a] == 0; m.face_hi[a] = eb[2 * a + 1] == g[a]; }
+  m.boxes = nullptr;
+}
+
+extern "C" mfe_ctx *mfe_create(int rank, int nranks, int device, const int global_box[6], const int *all_boxes)
+{
+  if (nranks < 1 || rank < 0 || rank >= nranks || !global_box || !all_boxes) { fail("mfe_create: bad arguments"); return nullptr; }
+  if (global_box[0] != 0 || global_box[2] != 0 || global_box[4] != 0 || global_box[1] < 1 || global_box[3] < 1 || global_box[5] < 1) {
+    fail("mfe_create: global box must be [0,nx)x[0,ny)x[0,nz)"); return nullptr;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev < 1) { cudaGetLastError(); fail("mfe_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e)); return nullptr; }
+  if (device < 0 || device >= ndev) { fail("mfe_create: device %d out of range (%d devices)", device, ndev); return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { fail("cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { fail("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return nullptr; }
+  if (prop.major < 10) { fail("mfe_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+  mfe_ctx *c = new mfe_ctx;
+  c->rank = rank; c->nranks = nranks; c->device = device; c->sm_count = prop.multiProcessorCount;
+  fill_mesh(c, global_box, all_boxes);
+  if (c->m.nrows < 1) { fail("mfe_create: rank %d owns no rows (ref/src/main.cpp:116-130 rejects such runs)", rank); delete c; return nullptr; }
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return nullptr; }
+  if (dev_alloc(&c->d_boxes, nranks)) { delete c; return nullptr; }
+  cudaMemcpy(c->d_boxes, c->boxes.data(), sizeof(RankBox) * nranks, cudaMemcpyHostToDevice);
+  c->m.boxes = c->d_boxes;
+  // element tables (Hex8_ElemData.hpp:37-61), computed on the host with the same single-rounding arithmetic
+  double grad[192], psi[64];
+  hex8_tables(grad, psi);
+  cudaMemcpyToSymbol(c_grad, grad, sizeof grad);
+  cudaMemcpyToSymbol(c_psi, psi, sizeof psi);
+  if (dev_alloc(&c->d_sc, 1) || dev_alloc(&c->d_gather, nranks)) { delete c; return nullptr; }
+  cudaMemset(c->d_sc, 0, sizeof(CgScalars));
+  if ((e = cudaGetLastError()) != cudaSuccess) { fail("mfe_create: %s", cudaGetErrorString(e)); delete c; return nullptr; }
+  return c;
+}
+
+static void free_matrix(mfe_ctx *c)
+{
+  free_dev(c->d_rows); free_dev(c->d_roff); free_dev(c->d_cols); free_dev(c->d_coefs); free_dev(c->d_tile_base);
+  c->d_rows = nullptr; c->d_roff = nullptr; c->d_cols = nullptr; c->d_coefs = nullptr; c->d_tile_base = nullptr;
+}
+static void free_vectors(mfe_ctx *c)
+{
+  free_dev(c->d_b); free_dev(c->d_x); free_dev(c->d_r); free_dev(c->d_p); free_dev(c->d_Ap); free_dev(c->d_tmp1); free_dev(c->d_tmp2);
+  free_dev(c->d_tile_sums); free_dev(c->dot.w.chunk_sums); free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps);
+  free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.chunk_tmp);
+  c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = c->d_tile_sums = nullptr;
+  c->dot = DotWs();
+  c->vec_cap = 0;
+}
+
+extern "C" void mfe_destroy(mfe_ctx *c)
+{
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  free_matrix(c); free_vectors(c);
+  free_dev(c->d_boxes); free_dev(c->d_sc); free_dev(c->d_hist); free_dev(c->d_gather);
+  free_dev(c->d_elements_to_send); free_dev(c->d_send_buf);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int mfe_comm_unique_id(char id128[128])
+{
+  if (nccl_load()) return 1;
+  ncclUniqueId_t id;
+  int r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail("ncclGetUniqueId: %s", nccl_errstr(r));
+  memcpy(id128, id.internal, 128);
+  return 0;
+}
+extern "C" int mfe_comm_init(mfe_ctx *c, const char id128[128])
+{
+  if (!c) return fail("null context");
+  if (c->nranks == 1) return 0;
+  if (nccl_load()) return 1;
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId_t id;
+  memcpy(id.internal, id128, 128);
+  CKN(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank));
+  return 0;
+}
+
+// vectors + dot workspace sized for (nrows, ncols)
+static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
+{
+  const int64_t need = std::max(nrows, ncols) + 8;
+  if (c->vec_cap >= need) return 0;
+  std::vector<double> keep_b, keep_x;
+  const bool keep = c->d_b != nullptr && c->vec_cap > 0;
+  double *ob = c->d_b, *ox = c->d_x;
+  c->d_b = c->d_x = nullptr;
+  const int64_t oldcap = c->vec_cap;
+  free_vectors(c);
+  if (dev_alloc(&c->d_b, need) || dev_alloc(&c->d_x, need) || dev_alloc(&c->d_r, need) || dev_alloc(&c->d_p, need) ||
+      dev_alloc(&c->d_Ap, need) || dev_alloc(&c->d_tmp1, need) || dev_alloc(&c->d_tmp2, need)) return 1;
+  CK(cudaMemsetAsync(c->d_b, 0, need * 8, c->stream)); CK(cudaMemsetAsync(c->d_x, 0, need * 8, c->stream));
+  CK(cudaMemsetAsync(c->d_r, 0, need * 8, c->stream)); CK(cudaMemsetAsync(c->d_p, 0, need * 8, c->stream));
+  CK(cudaMemsetAsync(c->d_Ap, 0, need * 8, c->stream));
+  if (keep) {
+    CK(cudaMemcpyAsync(c->d_b, ob, std::min(oldcap, need) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_x, ox, std::min(oldcap, need) * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  free_dev(ob); free_dev(ox);
+  const int64_t nchunks = (need + DOT_CHUNK - 1) / DOT_CHUNK;
+  const int64_t ntiles = (need + MV_TR - 1) / MV_TR;
+  if (dev_alloc(&c->d_tile_sums, ntiles + 1) || dev_alloc(&c->dot.w.chunk_sums, nchunks + 1) || dev_alloc(&c->dot.w.chunk_prefix, nchunks + 2) ||
+      dev_alloc(&c->dot.w.cta_maps, nchunks + 1) || dev_alloc(&c->dot.w.leaf_maps, (nchunks + 1) * DOT_CTA_THREADS) ||
+      dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) || dev_alloc(&c->dot.w.result, 1) ||
+      dev_alloc(&c->dot.chunk_tmp, nchunks + 1)) return 1;
+  CK(cudaMemsetAsync(c->dot.w.dirty_count, 0, sizeof(int), c->stream));
+  c->vec_cap = need;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------------------------------------
+struct PhaseTimer {
+  cudaEvent_t a = nullptr, b = nullptr; cudaStream_t s;
+  explicit PhaseTimer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+  double stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+  ~PhaseTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+static int build_tile_base(mfe_ctx *c)
+{
+  c->ntiles = (c->nrows + MV_TR - 1) / MV_TR;
+  free_dev(c->d_tile_base);
+  if (dev_alloc(&c->d_tile_base, c->ntiles + 2)) return 1;
+  if (c->mesh_csr) k_tile_base_mesh<<<grid_for(c->ntiles + 1, 256), 256, 0, c->stream>>>(c->m, MV_TR, c->ntiles, c->d_tile_base);
+  else k_tile_base_csr<<<grid_for(c->ntiles + 1, 256), 256, 0, c->stream>>>(c->d_roff, c->nrows, MV_TR, c->ntiles, c->d_tile_base);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mfe_generate_matrix_structure(mfe_ctx *c, int64_t *nrows, int64_t *first_row, int64_t *nnz)
+{
+  if (!c) return fail("null context");
+  CK(cudaSetDevice(c->device));
+  PhaseTimer tm(c->stream);
+  free_matrix(c);
+  c->mesh_csr = true; c->has_local = false;
+  c->nrows = c->m.nrows;
+  c->nnz = total_nnz_of(c->m);
+  c->nnz_padded = ((c->nnz + 3) & ~3LL) + 4;
+  c->num_cols = 0;
+  if (dev_alloc(&c->d_rows, c->nrows) || dev_alloc(&c->d_roff, c->nrows + 8) || dev_alloc(&c->d_cols, c->nnz_padded) ||
+      dev_alloc(&c->d_coefs, c->nnz_padded)) return 1;
+  CK(cudaMemsetAsync(c->d_cols, 0, c->nnz_padded * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->d_coefs, 0, c->nnz_padded * sizeof(double), c->stream));   // MatrixInitOp.hpp:147 coefs = 0
+  k_structure<<<grid_for(c->nrows, 128), 128, 0, c->stream>>>(c->m, c->d_rows, c->d_roff, c->d_cols);
+  c->launches++;
+  CK(cudaGetLastError());
+  if (build_tile_base(c)) return 1;
+  if (ensure_vectors(c, c->nrows, c->nrows)) return 1;
+  // Vector b, x are zero-filled on construction (Vector.hpp:44-52, driver.hpp:188-189)
+  CK(cudaMemsetAsync(c->d_b, 0, c->vec_cap * 8, c->stream));
+  CK(cudaMemsetAsync(c->d_x, 0, c->vec_cap * 8, c->stream));
+  c->t_structure = tm.stop();
+  CK(cudaGetLastError());
+  c->has_structure = true;
+  if (nrows) *nrows = c->nrows;
+  if (first_row) *first_row = c->m.first_row;
+  if (nnz) *nnz = c->nnz;
+  return 0;
+}
+
+extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
+{
+  if (!c || !c->has_structure || !c->mesh_csr) return fail("mfe_assemble_FE_data: call mfe_generate_matrix_structure first");
+  if (c->has_local) return fail("mfe_assemble_FE_data: matrix already has local indices");
+  CK(cudaSetDevice(c->device));
+  PhaseTimer tm(c->stream);
+  const MeshDesc &m = c->m;
+  // element box + ghost layer (assemble_FE_data.hpp:59-70)
+  int eb[6]; for (int i = 0; i < 6; ++i) eb[i] = m.eb[i];
+  if (eb[0] > 0) eb[0]--; if (eb[2] > 0) eb[2]--; if (eb[4] > 0) eb[4]--;
+  if (eb[1] < m.nx) eb[1]++; if (eb[3] < m.ny) eb[3]++; if (eb[5] < m.nz) eb[5]++;
+  const int nex = eb[1] - eb[0], ney = eb[3] - eb[2];
+  const int64_t eplane = (int64_t)nex * ney;
+  // node planes are processed in slabs so that the element scratch stays bounded (<= ~2 GiB)
+  int planes = (int)std::max<int64_t>(1, (int64_t)(2LL << 30) / (eplane * 44 * 8) - 1);
+  planes = std::min(planes, m.lnz);
+  ElemSlab sl; sl.ex0 = eb[0]; sl.ey0 = eb[2]; sl.nex = nex; sl.ney = ney; sl.stride = eplane * (planes + 1);
+  double *KF = nullptr;
+  if (dev_alloc(&KF, sl.stride * 44)) return 1;
+  cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+  double t_el = 0, t_ga = 0;
+  for (int iz0 = m.nb[4]; iz0 < m.nb[5]; iz0 += planes) {
+    const int iz1 = std::min(iz0 + planes, m.nb[5]);
+    const int ez0 = std::max(iz0 - 1, 0), ez1 = std::min(iz1, m.nz);     // element planes touching node planes [iz0,iz1)
+    sl.ez0 = ez0; sl.nez = ez1 - ez0;
+    cudaEventRecord(e0, c->stream);
+    const int64_t ne = eplane * sl.nez;
+    if (ne > 0) { k_elements<<<grid_for(ne, 128), 128, 0, c->stream>>>(m, sl, KF); c->launches++; }
+    cudaEventRecord(e1, c->stream);
+    const int64_t nr = (int64_t)m.lnx * m.lny * (iz1 - iz0);
+    k_gather_rows<<<grid_for(nr, 128), 128, 0, c->stream>>>(m, sl, KF, iz0, iz1, c->d_roff, c->d_tile_base, MV_TR, c->d_coefs, c->d_b);
+    c->launches++;
+    cudaEventRecord(e2, c->stream);
+    cudaEventSynchronize(e2);
+    float a = 0, b = 0; cudaEventElapsedTime(&a, e0, e1); cudaEventElapsedTime(&b, e1, e2);
+    t_el += a; t_ga += b;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+  c->t_assembly = tm.stop();
+  c->t_assembly_elem = t_el; c->t_assembly_gather = t_ga;
+  cudaFree(KF);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mfe_impose_dirichlet(mfe_ctx *c, double val, int which)
+{
+  if (!c || !c->has_structure || !c->mesh_csr) return fail("mfe_impose_dirichlet: no mesh matrix");
+  if (c->has_local) return fail("mfe_impose_dirichlet: must be called before mfe_make_local_matrix (columns must be global rows)");
+  if (which != 0 && which != 1) return fail("mfe_impose_dirichlet: which_set must be 0 or 1");
+  CK(cudaSetDevice(c->device));
+  PhaseTimer tm(c->stream);
+  k_dirichlet<<<grid_for(c->nrows, 128), 128, 0, c->stream>>>(c->m, which, val, c->d_roff, c->d_tile_base, MV_TR, c->d_cols, c->d_coefs, c->d_b);
+  c->launches++;
+  (which == 0 ? c->t_dir0 : c->t_dir1) = tm.stop();
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// make_local_matrix: ref/src/make_local_matrix.hpp:42-442.
+// The reference discovers externals by scanning rows (ascending) and their sorted columns, numbering each
+// external at first encounter.  For the 27-point stencil that order is closed-form: an external node E is
+// first met in the smallest adjacent owned row, first(E) = row(max(lo, E-1) per axis), and inside one row
+// externals appear in ascending global row.  So external_index = externals sorted by (first(E), globalrow(E)).
+// The peers' lists (-> elements_to_send) follow from the same rule applied to the peer's box: no messages.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
+{
+  if (!c || !c->has_structure) return fail("mfe_make_local_matrix: no matrix");
+  CK(cudaSetDevice(c->device));
+  PhaseTimer tm(c->stream);
+  c->external_index.clear(); c->external_local_index.clear(); c->elements_to_send.clear();
+  c->neighbors.clear(); c->recv_length.clear(); c->send_length.clear();
+  if (c->has_local) { if (num_cols) *num_cols = c->num_cols; return 0; }
+  if (c->nranks == 1) {              // make_local_matrix.hpp:51-55
+    c->num_cols = c->nrows; c->has_local = true;
+    c->t_make_local = tm.stop();
+    if (num_cols) *num_cols = c->num_cols;
+    return 0;
+  }
+  MeshDesc hm = c->m;                    // host view of the box table
+  hm.boxes = c->boxes.data();
+  LocalMaps L;
+  compute_local_maps(hm, L);
+  c->external_index = L.external_index; c->external_local_index = L.external_local_index;
+  c->elements_to_send = L.elements_to_send; c->neighbors = L.neighbors;
+  c->recv_length = L.recv_length; c->send_length = L.send_length;
+  c->num_cols = L.num_cols;
+  const int n_ext = (int)c->external_index.size();
+  // device: rewrite the columns (owned: col - start_row; external: external_local_index)
+  std::vector<std::pair<int, int>> srt(n_ext);
+  for (int i = 0; i < n_ext; ++i) srt[i] = { c->external_index[i], c->external_local_index[i] };
+  std::sort(srt.begin(), srt.end());
+  std::vector<int> sg(n_ext + 1), slc(n_ext + 1);
+  for (int i = 0; i < n_ext; ++i) { sg[i] = srt[i].first; slc[i] = srt[i].second; }
+  int *d_sg = nullptr, *d_sl = nullptr;
+  if (dev_alloc(&d_sg, n_ext + 1) || dev_alloc(&d_sl, n_ext + 1)) return 1;
+  CK(cudaMemcpyAsync(d_sg, sg.data(), sizeof(int) * (n_ext + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_sl, slc.data(), sizeof(int) * (n_ext + 1), cudaMemcpyHostToDevice, c->stream));
+  const int start_row = c->m.first_row, stop_row = c->m.first_row + (int)c->nrows - 1;
+  k_localize_cols<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_cols, c->nnz, start_row, stop_row, d_sg, d_sl, n_ext);
+  c->launches++;
+  free_dev(c->d_elements_to_send); free_dev(c->d_send_buf);
+  const int nsend = (int)c->elements_to_send.size();
+  if (dev_alloc(&c->d_elements_to_send, nsend + 1) || dev_alloc(&c->d_send_buf, nsend + 1)) return 1;
+  CK(cudaMemcpyAsync(c->d_elements_to_send, c->elements_to_send.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice, c->stream));
+  if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  c->t_make_local = tm.stop();
+  cudaFree(d_sg); cudaFree(d_sl);
+  CK(cudaGetLastError());
+  c->has_local = true;
+  if (num_cols) *num_cols = c->num_cols;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels launchers
+// ---------------------------------------------------------------------------------------------------------
+template <int TR, int G, int S>
+static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, double *tile_sums, const CgScalars *gate, int k)
+{
+  static bool attr_set[64] = { false };
+  const size_t smem = (size_t)G * S * MatvecCfg<TR>::SLOT_BYTES + (size_t)G * S * 8 + (size_t)G * (TR / 32) * 8 + 64;
+  auto kern = k_matvec<TR, G, S>;
+  if (!attr_set[c->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[c->device & 63] = true;
+  }
+  const int64_t groups_needed = c->ntiles;
+  int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (groups_needed + G - 1) / G));
+  kern<<<grid, TR * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded,
+                                          tile_sums, gate, k);
+  c->launches++;
+  return 0;
+}
+
+// halo exchange on the context stream: ref/src/exchange_externals.hpp:44-161
+static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+{
+  if (c->nranks == 1) return 0;
+  if (!c->comm) return fail("exchange_externals: nranks > 1 but mfe_comm_init was not called");
+  const int nsend = (int)c->elements_to_send.size();
+  if (nsend > 0) { k_pack<<<grid_for(nsend, 256), 256, 0, c->stream>>>(x, c->d_elements_to_send, nsend, c->d_send_buf, gate, k); c->launches++; }
+  CKN(g_nccl.GroupStart());
+  int64_t ro = c->nrows, so = 0;
+  for (size_t i = 0; i < c->neighbors.size(); ++i) {
+    if (c->recv_length[i] > 0) CKN(g_nccl.Recv(x + ro, (size_t)c->recv_length[i], NCCL_FLOAT64, c->neighbors[i], c->comm, c->stream));
+    if (c->send_length[i] > 0) CKN(g_nccl.Send(c->d_send_buf + so, (size_t)c->send_length[i], NCCL_FLOAT64, c->neighbors[i], c->comm, c->stream));
+    ro += c->recv_length[i]; so += c->send_length[i];
+  }
+  CKN(g_nccl.GroupEnd());
+  return 0;
+}
+
+static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k)
+{
+  if (exchange(c, x, gate, k)) return 1;
+  if (launch_matvec_cfg<MV_TR, 4, 2>(c, x, y, with_sums ? c->d_tile_sums : nullptr, gate, k)) return 1;
+  return 0;
+}
+
+static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, ScalarArg b, const double *y, double *w, const CgScalars *gate, int k)
+{
+  const int64_t n2 = std::max<int64_t>(1, n / 2);
+  const int grid = (int)std::min<int64_t>((n2 + 255) / 256, (int64_t)c->sm_count * 16);
+  k_waxpby<<<grid, 256, 0, c->stream>>>(n, a, x, b, y, w, gate, k);
+  c->launches++;
+}
+
+// local dot of x,y (n terms) + rank-ordered global sum + CG scalar epilogue.
+// sums_kind: 0 = none available (compute chunk sums here), 1 = chunk_sums already filled (k_xr_update),
+//            2 = SpMV tile sums available in d_tile_sums
+static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, int sums_kind, int epi, int k, bool gated, double *hist)
+{
+  const CgScalars *gate = gated ? c->d_sc : nullptr;
+  CgScalars *sc = c->d_sc;
+  double *nh = hist, *rh = hist ? hist + c->hist_cap : nullptr, *ph = hist ? hist + 2 * c->hist_cap : nullptr, *ah = hist ? hist + 3 * c->hist_cap : nullptr;
+  const int nchunks = (int)((n + DOT_CHUNK - 1) / DOT_CHUNK);
+  const bool multi = c->nranks > 1;
+  const int epi_local = multi ? EPI_NONE : epi;
+  DotWork &w = c->dot.w;
+  if (c->dot_mode == MFE_DOT_SERIAL) {
+    k_dot_serial<<<1, 1, 0, c->stream>>>(n, x, y, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
+    c->launches++;
+  } else {
+    if (sums_kind == 0) { if (nchunks > 0) { k_chunk_sums<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w.chunk_sums, gate, k); c->launches++; } }
+    if (sums_kind == 2) k_chunk_prefix<<<1, 1024, 0, c->stream>>>(c->d_tile_sums, DOT_CHUNK / MV_TR, (n + MV_TR - 1) / MV_TR, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
+    else k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, 1, nchunks, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
+    c->launches++;
+    if (c->dot_mode == MFE_DOT_TREE) {
+      k_dot_tree_finish<<<1, 1, 0, c->stream>>>(w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
+      c->launches++;
+    } else {
+      if (nchunks > 0) { k_dot_maps<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k); c->launches++; }
+      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
+      c->launches++;
+    }
+  }
+  if (multi) {
+    if (!c->comm) return fail("dot: nranks > 1 but mfe_comm_init was not called");
+    CKN(g_nccl.AllGather(w.result, c->d_gather, 1, NCCL_FLOAT64, c->comm, c->stream));
+    k_dot_allreduce_finish<<<1, 1, 0, c->stream>>>(c->d_gather, c->nranks, w.result, sc, epi, k, nh, rh, ph, ah, gate);
+    c->launches++;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// cg_solve: ref/src/cg_solve.hpp:69-229
+// ---------------------------------------------------------------------------------------------------------
+struct OpTimer {          // CUDA-event pairs per op class, resolved after the solve (no host sync inside)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
+  cudaStream_t s; bool on;
+  OpTimer(cudaStream_t st, bool enabled) : s(st), on(enabled) {}
+  void begin(int cls) { if (!on) return; cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); ev[cls].push_back({ a, b }); }
+  void end(int cls) { if (!on) return; cudaEventRecord(ev[cls].back().second, s); }
+  double total_s(int cls) {
+    double t = 0;
+    for (auto &p : ev[cls]) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); t += ms; cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    ev[cls].clear();
+    return t * 1e-3;
+  }
+};
+
+static int read_scalars(mfe_ctx *c, CgScalars *h)
+{
+  CK(cudaMemcpyAsync(h, c->d_sc, sizeof(CgScalars), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol, int *num_iters, double *normr, double cg_times[MFE_NUM_TIMERS],
+                            double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist)
+{
+  if (!c || !c->has_structure) return fail("mfe_cg_solve: no matrix");
+  if (!c->has_local) {   // cg_solve.hpp:99-104
+    fprintf(stderr, "miniFE::cg_solve ERROR, A.has_local_indices is false, needs to be true. This probably means "
+                    "miniFE::make_local_matrix(A) was not called prior to calling miniFE::cg_solve.\n");
+    return fail("mfe_cg_solve: make_local_matrix was not called");
+  }
+  if (max_iter < 0) return fail("mfe_cg_solve: max_iter < 0");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  const int64_t n = c->nrows;
+  if (c->hist_cap < max_iter + 1) {
+    free_dev(c->d_hist);
+    c->hist_cap = max_iter + 1;
+    if (dev_alloc(&c->d_hist, 4 * (int64_t)c->hist_cap)) return 1;
+  }
+  cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
+  cudaEventRecord(t0, c->stream);
+  if (x_host) CK(cudaMemcpyAsync(c->d_x, x_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+  k_fill<<<64, 256, 0, c->stream>>>(c->d_hist, 4 * (int64_t)c->hist_cap, std::numeric_limits<double>::quiet_NaN());
+  c->launches++;
+  CgScalars h{};
+  h.tol = tol; h.brkdown_tol = std::numeric_limits<double>::epsilon();
+  h.one = 1.0; h.zero = 0.0; h.neg_one = -1.0;
+  h.stop_iter = max_iter; h.status = CG_RUNNING; h.max_iter = max_iter;
+  CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  // r, p (num_cols), Ap start zero-filled (cg_solve.hpp:109-111)
+  CK(cudaMemsetAsync(c->d_r, 0, n * 8, c->stream));
+  CK(cudaMemsetAsync(c->d_p, 0, c->num_cols * 8, c->stream));
+  CK(cudaMemsetAsync(c->d_Ap, 0, n * 8, c->stream));
+
+  OpTimer ot(c->stream, c->op_timing != 0);
+  const ScalarArg one{ nullptr, 1.0 }, zero{ nullptr, 0.0 }, neg_one{ nullptr, -1.0 };
+  CgScalars *sc = c->d_sc;
+  double *hist = c->d_hist;
+
+  ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_x, zero, c->d_x, c->d_p, nullptr, 0); ot.end(MFE_WAXPY);           // p = x        (:124)
+  ot.begin(MFE_MATVEC); if (launch_matvec(c, c->d_p, c->d_Ap, false, nullptr, 0)) return 1; ot.end(MFE_MATVEC);         // Ap = A p     (:129)
+  ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_b, neg_one, c->d_Ap, c->d_r, nullptr, 0); ot.end(MFE_WAXPY);       // r = b - Ap   (:132)
+  ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_r, c->d_r, 0, EPI_INIT_RR, 0, false, hist)) return 1; ot.end(MFE_DOT);   // rtrans       (:134)
+
+  int rc = 0;
+  int k = 1;
+  int resume_phase = 0;      // 0: start of iteration k, 1: after the p_ap dot of iteration k (breakdown pause resolved)
+  while (k <= max_iter) {
+    const int k_batch_end = std::min(max_iter, k + 24);
+    for (; k <= k_batch_end; ++k) {
+      if (resume_phase == 0) {
+        if (k == 1) {
+          ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_r, zero, c->d_r, c->d_p, sc, k); ot.end(MFE_WAXPY);        // p = r (:154)
+        } else {
+          ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_r, c->d_r, 1, EPI_RR, k, true, hist)) return 1; ot.end(MFE_DOT); // (:158)
+          ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_r, ScalarArg{ &sc->beta, 0.0 }, c->d_p, c->d_p, sc, k); ot.end(MFE_WAXPY);  // (:160)
+        }
+        ot.begin(MFE_MATVEC); if (launch_matvec(c, c->d_p, c->d_Ap, c->dot_mode != MFE_DOT_SERIAL, sc, k)) return 1; ot.end(MFE_MATVEC);   // (:177)
+        ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_Ap, c->d_p, c->dot_mode != MFE_DOT_SERIAL ? 2 : 0, EPI_PAP, k, true, hist)) return 1; ot.end(MFE_DOT);  // (:179)
+      }
+      resume_phase = 0;
+      ot.begin(MFE_WAXPY);                                                                                               // (:211-212)
+      k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.w.chunk_sums, sc, k);
+      c->launches++;
+      ot.end(MFE_WAXPY);
+    }
+    if (read_scalars(c, &h)) return 1;
+    if (h.status == CG_PAUSED) {
+      // cg_solve.hpp:186-200: p_ap_dot < brkdown_tol and >= 0  ->  breakdown(p_ap_dot, Ap, p)  (cg_solve.hpp:49-67)
+      const int kp = h.pause_iter;
+      double vv = 0, ww = 0;
+      if (launch_dot(c, n, c->d_Ap, c->d_Ap, 0, EPI_NONE, 0, false, nullptr)) return 1;
+      CK(cudaMemcpyAsync(&vv, c->dot.w.result, 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+      if (launch_dot(c, n, c->d_p, c->d_p, 0, EPI_NONE, 0, false, nullptr)) return 1;
+      CK(cudaMemcpyAsync(&ww, c->dot.w.result, 8, cudaMemcpyDeviceToHost, c->stream)); CK(cudaStreamSynchronize(c->stream));
+      const double vnorm = std::sqrt(vv), wnorm = std::sqrt(ww);
+      const bool brk = std::fabs(h.p_ap_dot) <= 100 * vnorm * wnorm * std::numeric_limits<double>::epsilon();
+      if (brk) { h.status = CG_BREAKDOWN; h.stop_iter = kp - 1; CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream)); }
+      else {
+        h.brkdown_tol = 0.1 * h.p_ap_dot;
+        h.alpha = h.rtrans / h.p_ap_dot; h.neg_alpha = -h.alpha;
+        h.status = CG_RUNNING; h.stop_iter = max_iter;
+        // the loop test that the convergence epilogue would have applied for iteration kp
+        if (!(h.normr > h.tol)) { h.stop_iter = kp; h.status = CG_CONVERGED; }
+        CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->d_hist + 3 * c->hist_cap + kp, &h.alpha, 8, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        k = kp; resume_phase = 1;
+        continue;
+      }
+    }
+    if (h.status == CG_BREAKDOWN) {
+      fprintf(stderr, "miniFE::cg_solve ERROR, numerical breakdown!\n");
+      rc = 1;
+      break;
+    }
+    if (h.status == CG_CONVERGED || h.stop_iter < k) break;
+  }
+  if (read_scalars(c, &h)) return 1;
+  cudaEventRecord(t1, c->stream);
+  if (x_host) CK(cudaMemcpyAsync(x_host, c->d_x, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<double> hh(4 * (size_t)c->hist_cap);
+  CK(cudaMemcpyAsync(hh.data(), c->d_hist, hh.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0; cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0); cudaEventDestroy(t1);
+  c->t_cg = ms;
+  const int iters = std::min(h.stop_iter, max_iter);
+  if (num_iters) *num_iters = iters;
+  if (normr) *normr = h.normr;
+  if (cg_times) {
+    cg_times[MFE_WAXPY] = ot.total_s(MFE_WAXPY); cg_times[MFE_DOT] = ot.total_s(MFE_DOT); cg_times[MFE_MATVEC] = ot.total_s(MFE_MATVEC);
+    cg_times[MFE_MATVECDOT] = 0; cg_times[MFE_TOTAL] = ms * 1e-3;
+  } else { ot.total_s(0); ot.total_s(1); ot.total_s(2); }
+  const size_t cap = c->hist_cap, cnt = (size_t)max_iter + 1;
+  if (normr_hist) memcpy(normr_hist, hh.data(), cnt * 8);
+  if (rtrans_hist) memcpy(rtrans_hist, hh.data() + cap, cnt * 8);
+  if (pap_hist) memcpy(pap_hist, hh.data() + 2 * cap, cnt * 8);
+  if (alpha_hist) memcpy(alpha_hist, hh.data() + 3 * cap, cnt * 8);
+  CK(cudaGetLastError());
+  return rc;
+}
+
+extern "C" int mfe_set_dot_mode(mfe_ctx *c, int mode)
+{
+  if (!c || mode < 0 || mode > 2) return fail("mfe_set_dot_mode: bad arguments");
+  c->dot_mode = mode;
+  return 0;
+}
+extern "C" int mfe_set_op_timing(mfe_ctx *c, int on) { if (!c) return fail("null context"); c->op_timing = on; return 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer kernel entry points
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mfe_matvec(mfe_ctx *c, double *x_host, double *y_host)
+{
+  if (!c || !c->has_structure || !c->has_local) return fail("mfe_matvec: matrix needs local indices (mfe_make_local_matrix)");
+  if (!x_host || !y_host) return fail("mfe_matvec: null buffer");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  CK(cudaMemcpyAsync(c->d_tmp1, x_host, c->num_cols * 8, cudaMemcpyHostToDevice, c->stream));
+  if (launch_matvec(c, c->d_tmp1, c->d_tmp2, false, nullptr, 0)) return 1;
+  CK(cudaMemcpyAsync(y_host, c->d_tmp2, c->nrows * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks > 1) CK(cudaMemcpyAsync(x_host + c->nrows, c->d_tmp1 + c->nrows, (c->num_cols - c->nrows) * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mfe_exchange_externals(mfe_ctx *c, double *x_host)
+{
+  if (!c || !c->has_local) return fail("mfe_exchange_externals: matrix needs local indices");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  CK(cudaMemcpyAsync(c->d_tmp1, x_host, c->num_cols * 8, cudaMemcpyHostToDevice, c->stream));
+  if (exchange(c, c->d_tmp1, nullptr, 0)) return 1;
+  CK(cudaMemcpyAsync(x_host, c->d_tmp1, c->num_cols * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int mfe_waxpby(mfe_ctx *c, int64_t n, double alpha, const double *x_host, double beta, const double *y_host, double *w_host)
+{
+  if (!c || n < 0) return fail("mfe_waxpby: bad arguments");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, n, n)) return 1;
+  double *dw = c->d_r;   // scratch: r is rebuilt by every cg_solve
+  CK(cudaMemcpyAsync(c->d_tmp1, x_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_tmp2, y_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+  launch_waxpby(c, n, ScalarArg{ nullptr, alpha }, c->d_tmp1, ScalarArg{ nullptr, beta }, c->d_tmp2, dw, nullptr, 0);
+  CK(cudaMemcpyAsync(w_host, dw, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mfe_dot(mfe_ctx *c, int64_t n, const double *x_host, const double *y_host, double *result)
+{
+  if (!c || n < 0 || !result) return fail("mfe_dot: bad arguments");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, n, n)) return 1;
+  CK(cudaMemcpyAsync(c->d_tmp1, x_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_tmp2, y_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+  if (launch_dot(c, n, c->d_tmp1, c->d_tmp2, 0, EPI_NONE, 0, false, nullptr)) return 1;
+  CK(cudaMemcpyAsync(result, c->dot.w.result, 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// queries / import / export
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int64_t mfe_nrows(const mfe_ctx *c) { return c ? c->nrows : -1; }
+extern "C" int64_t mfe_first_row(const mfe_ctx *c) { return c ? (c->nrows > 0 ? c->m.first_row : -1) : -1; }
+extern "C" int64_t mfe_nnz(const mfe_ctx *c) { return c ? c->nnz : -1; }
+extern "C" int64_t mfe_num_cols(const mfe_ctx *c) { return c ? c->num_cols : -1; }
+extern "C" int64_t mfe_launch_count(const mfe_ctx *c) { return c ? c->launches : -1; }
+
+extern "C" int64_t mfe_get_map(const mfe_ctx *c, const char *name, int *out)
+{
+  if (!c || !name) return -1;
+  const std::vector<int> *v = nullptr;
+  if (!strcmp(name, "external_index")) v = &c->external_index;
+  else if (!strcmp(name, "external_local_index")) v = &c->external_local_index;
+  else if (!strcmp(name, "elements_to_send")) v = &c->elements_to_send;
+  else if (!strcmp(name, "neighbors")) v = &c->neighbors;
+  else if (!strcmp(name, "recv_length")) v = &c->recv_length;
+  else if (!strcmp(name, "send_length")) v = &c->send_length;
+  else return -1;
+  if (out && !v->empty()) memcpy(out, v->data(), v->size() * sizeof(int));
+  return (int64_t)v->size();
+}
+
+extern "C" int mfe_export_csr(mfe_ctx *c, int *rows, int *row_offsets, int64_t *row_offsets64, int *cols, double *coefs)
+{
+  if (!c || !c->has_structure) return fail("mfe_export_csr: no matrix");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  if (rows) CK(cudaMemcpy(rows, c->d_rows, c->nrows * sizeof(int), cudaMemcpyDeviceToHost));
+  if (row_offsets) {
+    if (c->nnz > 0x7fffffffLL) return fail("mfe_export_csr: nnz=%lld overflows 32-bit row_offsets; use row_offsets64", (long long)c->nnz);
+    CK(cudaMemcpy(row_offsets, c->d_roff, (c->nrows + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (row_offsets64) {
+    std::vector<uint32_t> lo(c->nrows + 1);
+    std::vector<int64_t> tb(c->ntiles + 1);
+    CK(cudaMemcpy(lo.data(), c->d_roff, (c->nrows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tb.data(), c->d_tile_base, (c->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    for (int64_t r = 0; r <= c->nrows; ++r) {
+      const int64_t t = std::min(r / MV_TR, c->ntiles - 1);
+      row_offsets64[r] = tb[t] + (int64_t)(uint32_t)(lo[r] - lo[t * MV_TR]);
+    }
+  }
+  if (cols) CK(cudaMemcpy(cols, c->d_cols, c->nnz * sizeof(int), cudaMemcpyDeviceToHost));
+  if (coefs) CK(cudaMemcpy(coefs, c->d_coefs, c->nnz * sizeof(double), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+static double *vec_by_name(mfe_ctx *c, const char *name)
+{
+  if (!name) return nullptr;
+  if (!strcmp(name, "b")) return c->d_b;
+  if (!strcmp(name, "x")) return c->d_x;
+  return nullptr;
+}
+extern "C" int mfe_export_vector(mfe_ctx *c, const char *name, double *out)
+{
+  if (!c || !out) return fail("mfe_export_vector: bad arguments");
+  double *d = vec_by_name(c, name);
+  if (!d) return fail("mfe_export_vector: unknown vector '%s'", name ? name : "(null)");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out, d, c->nrows * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+extern "C" int mfe_import_vector(mfe_ctx *c, const char *name, const double *in)
+{
+  if (!c || !in) return fail("mfe_import_vector: bad arguments");
+  double *d = vec_by_name(c, name);
+  if (!d) return fail("mfe_import_vector: unknown vector '%s'", name ? name : "(null)");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(d, in, c->nrows * 8, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+extern "C" int mfe_import_csr(mfe_ctx *c, int64_t nrows, int64_t num_cols, const int *row_offsets, const int *cols, const double *coefs)
+{
+  if (!c || nrows < 1 || num_cols < nrows || !row_offsets || !cols || !coefs) return fail("mfe_import_csr: bad arguments");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  free_matrix(c);
+  c->mesh_csr = false;
+  c->nrows = nrows; c->nnz = row_offsets[nrows]; c->num_cols = num_cols;
+  c->nnz_padded = ((c->nnz + 3) & ~3LL) + 4;
+  if (dev_alloc(&c->d_rows, nrows) || dev_alloc(&c->d_roff, nrows + 8) || dev_alloc(&c->d_cols, c->nnz_padded) || dev_alloc(&c->d_coefs, c->nnz_padded)) return 1;
+  std::vector<int> rows(nrows);
+  for (int64_t i = 0; i < nrows; ++i) rows[i] = c->m.first_row + (int)i;
+  CK(cudaMemset(c->d_cols, 0, c->nnz_padded * sizeof(int)));
+  CK(cudaMemset(c->d_coefs, 0, c->nnz_padded * sizeof(double)));
+  CK(cudaMemcpy(c->d_rows, rows.data(), nrows * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_roff, row_offsets, (nrows + 1) * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_cols, cols, c->nnz * sizeof(int), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_coefs, coefs, c->nnz * sizeof(double), cudaMemcpyHostToDevice));
+  if (build_tile_base(c)) return 1;
+  if (ensure_vectors(c, nrows, num_cols)) return 1;
+  CK(cudaStreamSynchronize(c->stream));
+  c->has_structure = true; c->has_local = true;
+  return 0;
+}
+
+extern "C" double mfe_phase_ms(const mfe_ctx *c, const char *phase)
+{
+  if (!c || !phase) return -1;
+  if (!strcmp(phase, "structure")) return c->t_structure;
+  if (!strcmp(phase, "assembly")) return c->t_assembly;
+  if (!strcmp(phase, "assembly_elem")) return c->t_assembly_elem;
+  if (!strcmp(phase, "assembly_gather")) return c->t_assembly_gather;
+  if (!strcmp(phase, "dirichlet0")) return c->t_dir0;
+  if (!strcmp(phase, "dirichlet1")) return c->t_dir1;
+  if (!strcmp(phase, "make_local")) return c->t_make_local;
+  if (!strcmp(phase, "cg")) return c->t_cg;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// timed repetitions of single kernels on the device-resident CG state (bench.py roofline, ncu captures)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *ms_per_launch)
+{
+  if (!c || !what || reps < 1 || !ms_per_launch) return fail("mfe_time_kernel: bad arguments");
+  if (!c->has_local) return fail("mfe_time_kernel: matrix needs local indices");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  const int64_t n = c->nrows;
+  const ScalarArg one{ nullptr, 1.0 }, half{ nullptr, 0.5 };
+  CgScalars h{}; h.alpha = 1e-3; h.neg_alpha = -1e-3; h.beta = 0.5; h.stop_iter = 1 << 30; h.tol = 0; h.one = 1; h.neg_one = -1;
+  h.rtrans = 1; h.oldrtrans = 1; h.brkdown_tol = -1e300;
+  CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  auto body = [&](int rep) -> int {
+    if (!strcmp(what, "matvec")) return launch_matvec_cfg<MV_TR, 4, 2>(c, c->d_p, c->d_Ap, nullptr, nullptr, 0);
+    if (!strcmp(what, "matvec_dot")) return launch_matvec_cfg<MV_TR, 4, 2>(c, c->d_p, c->d_Ap, c->d_tile_sums, nullptr, 0);
+    if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, MV_TR, c->d_p, c->d_Ap, n); c->launches++; return 0; }
+    if (!strcmp(what, "waxpby")) { launch_waxpby(c, n, one, c->d_r, half, c->d_p, c->d_tmp1, nullptr, 0); return 0; }
+    if (!strcmp(what, "dot_rr")) return launch_dot(c, n, c->d_r, c->d_r, 0, EPI_NONE, 0, false, nullptr);
+    if (!strcmp(what, "dot_pap")) return launch_dot(c, n, c->d_Ap, c->d_p, 0, EPI_NONE, 0, false, nullptr);
+    if (!strcmp(what, "xr_update")) { k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.w.chunk_sums, nullptr, 0); c->launches++; return 0; }
+    (void)rep;
+    return fail("mfe_time_kernel: unknown kernel '%s'", what);
+  };
+  if (body(-1)) return 1;                       // warm-up
+  CK(cudaStreamSynchronize(c->stream));
+  cudaEventRecord(a, c->stream);
+  for (int i = 0; i < reps; ++i) if (body(i)) return 1;
+  cudaEventRecord(b, c->stream);
+  CK(cudaEventSynchronize(b));
+  float ms = 0; cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a); cudaEventDestroy(b);
+  *ms_per_launch = ms / reps;
+  CK(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,101 @@
+// halo_maps.h -- host-side index maps of make_local_matrix (ref/src/make_local_matrix.hpp:42-442), computed
+// without messages.  The reference discovers externals by scanning rows (ascending) and their sorted columns,
+// numbering each external at first encounter.  For the 27-point stencil that order is closed-form: an external
+// node E is first met in the smallest adjacent owned row, first(E) = row(max(lo, E-1) per axis), and inside one
+// row externals appear in ascending global row.  So external_index = externals sorted by (first(E), globalrow(E)).
+// The peers' lists (-> elements_to_send) follow from the same rule applied to the peer's box.
+#pragma once
+#include <algorithm>
+#include <vector>
+#include "mesh.h"
+
+namespace mfe {
+
+struct ExtEntry { int64_t first; int grow; int owner; };
+
+struct LocalMaps {
+  std::vector<int> external_index, external_local_index, elements_to_send, neighbors, recv_length, send_length;
+  int64_t num_cols = 0;
+};
+
+// externals of rank p (nodes of the one-node shell around p's node box, owned by someone else), in the
+// reference's first-encounter order.  `gm.boxes` must be a HOST table.
+inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
+{
+  const RankBox &B = gm.boxes[p];
+  out.clear();
+  if (B.nrows == 0) return;
+  MeshDesc m = gm;
+  m.rank = p;
+  for (int i = 0; i < 6; ++i) m.nb[i] = B.nb[i];
+  m.lnx = B.nb[1] - B.nb[0]; m.lny = B.nb[3] - B.nb[2]; m.lnz = B.nb[5] - B.nb[4];
+  m.first_row = B.first_row; m.nrows = B.nrows;
+  const int lo[3] = { std::max(B.nb[0] - 1, 0), std::max(B.nb[2] - 1, 0), std::max(B.nb[4] - 1, 0) };
+  const int hi[3] = { std::min(B.nb[1] + 1, gm.gnx), std::min(B.nb[3] + 1, gm.gny), std::min(B.nb[5] + 1, gm.gnz) };
+  auto add = [&](int x, int y, int z) {
+    ExtEntry e;
+    const int fx = std::max(B.nb[0], x - 1), fy = std::max(B.nb[2], y - 1), fz = std::max(B.nb[4], z - 1);
+    e.first = (int64_t)(fx - B.nb[0]) + (int64_t)m.lnx * ((fy - B.nb[2]) + (int64_t)m.lny * (fz - B.nb[4]));
+    int ox, oy, oz;
+    e.grow = node_to_row(m, x, y, z);
+    e.owner = row_to_node(m, e.grow, ox, oy, oz);
+    out.push_back(e);
+  };
+  for (int z = lo[2]; z < hi[2]; ++z)
+    for (int y = lo[1]; y < hi[1]; ++y) {
+      const bool yz_inside = y >= B.nb[2] && y < B.nb[3] && z >= B.nb[4] && z < B.nb[5];
+      if (!yz_inside) { for (int x = lo[0]; x < hi[0]; ++x) add(x, y, z); }
+      else {
+        if (lo[0] < B.nb[0]) add(B.nb[0] - 1, y, z);
+        if (hi[0] > B.nb[1]) add(B.nb[1], y, z);
+      }
+    }
+  std::sort(out.begin(), out.end(), [](const ExtEntry &a, const ExtEntry &b) { return a.first != b.first ? a.first < b.first : a.grow < b.grow; });
+}
+
+// group by owner in first-encounter order of owners, encounter order inside a group (make_local_matrix.hpp:153-166)
+inline void group_externals(const std::vector<ExtEntry> &ext, std::vector<int> &owners, std::vector<std::vector<int>> &groups)
+{
+  owners.clear(); groups.clear();
+  for (size_t i = 0; i < ext.size(); ++i) {
+    size_t g = 0;
+    for (; g < owners.size(); ++g) if (owners[g] == ext[i].owner) break;
+    if (g == owners.size()) { owners.push_back(ext[i].owner); groups.emplace_back(); }
+    groups[g].push_back((int)i);
+  }
+}
+
+// all CSRMatrix index-map fields (ref/src/CSRMatrix.hpp:73-78) of rank gm.rank
+inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
+{
+  L = LocalMaps();
+  const int rank = gm.rank;
+  const int nrows = gm.boxes[rank].nrows, first_row = gm.boxes[rank].first_row;
+  std::vector<ExtEntry> ext;
+  externals_of(gm, rank, ext);
+  std::vector<int> owners; std::vector<std::vector<int>> groups;
+  group_externals(ext, owners, groups);
+  const int n_ext = (int)ext.size();
+  L.external_index.resize(n_ext); L.external_local_index.assign(n_ext, -1);
+  for (int i = 0; i < n_ext; ++i) L.external_index[i] = ext[i].grow;
+  int count = nrows;
+  for (size_t g = 0; g < owners.size(); ++g) {
+    L.neighbors.push_back(owners[g]);
+    L.recv_length.push_back((int)groups[g].size());
+    for (int i : groups[g]) L.external_local_index[i] = count++;
+  }
+  // what each neighbour needs from me, in ITS external order (make_local_matrix.hpp:386-429)
+  L.send_length.assign(L.neighbors.size(), 0);
+  std::vector<ExtEntry> pext; std::vector<int> pown; std::vector<std::vector<int>> pgrp;
+  for (size_t i = 0; i < L.neighbors.size(); ++i) {
+    externals_of(gm, L.neighbors[i], pext);
+    group_externals(pext, pown, pgrp);
+    for (size_t g = 0; g < pown.size(); ++g) if (pown[g] == rank) {
+      L.send_length[i] = (int)pgrp[g].size();
+      for (int e : pgrp[g]) L.elements_to_send.push_back(pext[e].grow - first_row);
+    }
+  }
+  L.num_cols = (int64_t)nrows + n_ext;
+}
+
+}  // namespace mfe

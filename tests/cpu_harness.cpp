@@ -1,0 +1,295 @@
+// tests/cpu_harness.cpp -- TEST INFRASTRUCTURE.  Runs the host+device-shared (MFE_HD) building blocks of the CUDA
+// kernels on the CPU, thread by thread, so that their logic (analytic mesh maps, element arithmetic order,
+// row-owner gather, Dirichlet rows, halo index maps, order-reproducing dot) can be checked against the oracle
+// without a GPU.  It is NOT a product path: nothing in minife_b200/ links or loads it, and the library has
+// no CPU fallback.  Built by tests/conftest.py:  g++ -O2 -ffp-contract=off -shared -fPIC.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+
+#include "../minife_b200/csrc/mesh.h"
+#include "../minife_b200/csrc/hex8.h"
+#include "../minife_b200/csrc/assembly.h"
+#include "../minife_b200/csrc/exact_dot.h"
+#include "../minife_b200/csrc/halo_maps.h"
+
+using namespace mfe;
+
+struct Harness {
+  MeshDesc m;
+  std::vector<RankBox> boxes;
+  std::vector<int> rows, cols;
+  std::vector<int64_t> roff;
+  std::vector<double> coefs, b;
+  LocalMaps maps;
+};
+
+static void rcb(int ip, int up, int axis, const int *box, int *out)
+{
+  const int np = up - ip;
+  if (np == 1) { for (int i = 0; i < 6; ++i) out[6 * ip + i] = box[i]; return; }
+  const int n = box[2 * axis + 1] - box[2 * axis];
+  const int np_low = np / 2, np_upp = np - np_low;
+  const int n_upp = (int)(((double)n) * (((double)np_upp) / ((double)np)));
+  const int n_low = n - n_upp, next = (axis + 2) % 3;
+  int lowb[6], uppb[6];
+  for (int i = 0; i < 6; ++i) lowb[i] = uppb[i] = box[i];
+  lowb[2 * axis + 1] = box[2 * axis] + n_low;
+  uppb[2 * axis] = box[2 * axis] + n_low;
+  uppb[2 * axis + 1] = uppb[2 * axis] + n_upp;
+  if (np_low) rcb(ip, ip + np_low, next, lowb, out);
+  rcb(ip + np_low, up, next, uppb, out);
+}
+
+extern "C" {
+
+void *hs_create(int nx, int ny, int nz, int np, int rank)
+{
+  Harness *h = new Harness;
+  std::vector<int> all(6 * np);
+  const int g[6] = { 0, nx, 0, ny, 0, nz };
+  rcb(0, np, 2, g, all.data());
+  MeshDesc &m = h->m;
+  m.nx = nx; m.ny = ny; m.nz = nz; m.gnx = nx + 1; m.gny = ny + 1; m.gnz = nz + 1;
+  m.nranks = np; m.rank = rank;
+  const int gg[3] = { nx, ny, nz };
+  h->boxes.resize(np);
+  int off = 0;
+  for (int p = 0; p < np; ++p) {
+    RankBox &b = h->boxes[p];
+    const int *eb = &all[6 * p];
+    for (int a = 0; a < 3; ++a) {
+      b.nb[2 * a] = eb[2 * a];
+      b.nb[2 * a + 1] = eb[2 * a + 1] + ((eb[2 * a + 1] > eb[2 * a] && eb[2 * a + 1] == gg[a]) ? 1 : 0);
+    }
+    b.nrows = (b.nb[1] - b.nb[0]) * (b.nb[3] - b.nb[2]) * (b.nb[5] - b.nb[4]);
+    b.first_row = off; off += b.nrows;
+  }
+  const int *eb = &all[6 * rank];
+  for (int i = 0; i < 6; ++i) { m.eb[i] = eb[i]; m.nb[i] = h->boxes[rank].nb[i]; }
+  m.lnx = m.nb[1] - m.nb[0]; m.lny = m.nb[3] - m.nb[2]; m.lnz = m.nb[5] - m.nb[4];
+  m.first_row = h->boxes[rank].first_row; m.nrows = h->boxes[rank].nrows;
+  for (int a = 0; a < 3; ++a) { m.face_lo[a] = eb[2 * a] == 0; m.face_hi[a] = eb[2 * a + 1] == gg[a]; }
+  m.boxes = h->boxes.data();
+  return h;
+}
+void hs_destroy(void *p) { delete (Harness *)p; }
+long long hs_nrows(void *p) { return ((Harness *)p)->m.nrows; }
+long long hs_nnz(void *p) { return total_nnz_of(((Harness *)p)->m); }
+
+// k_structure, one "thread" per row
+void hs_structure(void *p)
+{
+  Harness *h = (Harness *)p; const MeshDesc &m = h->m;
+  const int64_t nnz = total_nnz_of(m);
+  h->rows.assign(m.nrows, 0); h->roff.assign(m.nrows + 1, 0); h->cols.assign(nnz, -7); h->coefs.assign(nnz, 0.0); h->b.assign(m.nrows, 0.0);
+  for (int64_t lr = 0; lr < m.nrows; ++lr) {
+    int ix, iy, iz; local_row_to_node(m, lr, ix, iy, iz);
+    const int64_t off = row_offset_of(m, ix, iy, iz);
+    h->rows[lr] = m.first_row + (int)lr; h->roff[lr] = off;
+    int c[27]; unsigned char s[27];
+    const int len = row_columns(m, ix, iy, iz, c, s);
+    for (int j = 0; j < len; ++j) h->cols[off + j] = c[j];
+    if (lr == m.nrows - 1) h->roff[m.nrows] = off + len;
+  }
+}
+
+// k_elements + k_gather_rows, slabs of `planes` node planes
+void hs_assemble(void *p, int planes)
+{
+  Harness *h = (Harness *)p; const MeshDesc &m = h->m;
+  double grad[192], psi[64];
+  hex8_tables(grad, psi);
+  int eb[6]; for (int i = 0; i < 6; ++i) eb[i] = m.eb[i];
+  if (eb[0] > 0) eb[0]--; if (eb[2] > 0) eb[2]--; if (eb[4] > 0) eb[4]--;
+  if (eb[1] < m.nx) eb[1]++; if (eb[3] < m.ny) eb[3]++; if (eb[5] < m.nz) eb[5]++;
+  ElemSlab sl; sl.ex0 = eb[0]; sl.ey0 = eb[2]; sl.nex = eb[1] - eb[0]; sl.ney = eb[3] - eb[2];
+  const int64_t eplane = (int64_t)sl.nex * sl.ney;
+  if (planes < 1) planes = 1;
+  sl.stride = eplane * (planes + 1);
+  std::vector<double> KF(sl.stride * 44);
+  for (int iz0 = m.nb[4]; iz0 < m.nb[5]; iz0 += planes) {
+    const int iz1 = std::min(iz0 + planes, m.nb[5]);
+    const int ez0 = std::max(iz0 - 1, 0), ez1 = std::min(iz1, m.nz);
+    sl.ez0 = ez0; sl.nez = ez1 - ez0;
+    const int64_t ne = eplane * sl.nez;
+    for (int64_t e = 0; e < ne; ++e) {
+      const int ex = sl.ex0 + (int)(e % sl.nex), ey = sl.ey0 + (int)((e / sl.nex) % sl.ney), ez = sl.ez0 + (int)(e / eplane);
+      const double x = (double)ex / (double)m.nx, y = (double)ey / (double)m.ny, z = (double)ez / (double)m.nz;
+      const double hx = 1.0 / (double)m.nx, hy = 1.0 / (double)m.ny, hz = 1.0 / (double)m.nz;
+      double K[36], f[8];
+      hex8_element(grad, psi, x, y, z, hx, hy, hz, K, f);
+      for (int k = 0; k < 36; ++k) KF[(int64_t)k * sl.stride + e] = K[k];
+      for (int k = 0; k < 8; ++k) KF[(int64_t)(36 + k) * sl.stride + e] = f[k];
+    }
+    const int64_t plane = (int64_t)m.lnx * m.lny;
+    for (int64_t idx = 0; idx < plane * (iz1 - iz0); ++idx) {
+      const int64_t lr = (int64_t)(iz0 - m.nb[4]) * plane + idx;
+      int ix, iy, iz; local_row_to_node(m, lr, ix, iy, iz);
+      double acc[27], bsum;
+      gather_row(m, sl, KF.data(), ix, iy, iz, acc, bsum);
+      h->b[lr] = bsum;
+      store_row(m, ix, iy, iz, h->roff[lr], acc, h->coefs.data());
+    }
+  }
+}
+
+void hs_dirichlet(void *p, int which, double val)
+{
+  Harness *h = (Harness *)p; const MeshDesc &m = h->m;
+  for (int64_t lr = 0; lr < m.nrows; ++lr) {
+    int ix, iy, iz; local_row_to_node(m, lr, ix, iy, iz);
+    if (!dirichlet_touches(m, which, ix, iy, iz)) continue;
+    dirichlet_row(m, which, val, lr, ix, iy, iz, h->roff[lr], (int)(h->roff[lr + 1] - h->roff[lr]), h->cols.data(), h->coefs.data(), h->b.data());
+  }
+}
+
+// compute_local_maps + k_localize_cols
+void hs_make_local(void *p)
+{
+  Harness *h = (Harness *)p; const MeshDesc &m = h->m;
+  if (m.nranks == 1) { h->maps = LocalMaps(); h->maps.num_cols = m.nrows; return; }
+  compute_local_maps(m, h->maps);
+  const int n_ext = (int)h->maps.external_index.size();
+  std::vector<std::pair<int, int>> srt(n_ext);
+  for (int i = 0; i < n_ext; ++i) srt[i] = { h->maps.external_index[i], h->maps.external_local_index[i] };
+  std::sort(srt.begin(), srt.end());
+  const int start = m.first_row, stop = m.first_row + m.nrows - 1;
+  for (size_t i = 0; i < h->cols.size(); ++i) {
+    const int c = h->cols[i];
+    if (c >= start && c <= stop) { h->cols[i] = c - start; continue; }
+    auto it = std::lower_bound(srt.begin(), srt.end(), std::make_pair(c, -1));
+    h->cols[i] = (it != srt.end() && it->first == c) ? it->second : -1;
+  }
+}
+
+void hs_get_csr(void *p, int *rows, long long *roff, int *cols, double *coefs, double *b)
+{
+  Harness *h = (Harness *)p;
+  if (rows) memcpy(rows, h->rows.data(), h->rows.size() * sizeof(int));
+  if (roff) for (size_t i = 0; i < h->roff.size(); ++i) roff[i] = h->roff[i];
+  if (cols) memcpy(cols, h->cols.data(), h->cols.size() * sizeof(int));
+  if (coefs) memcpy(coefs, h->coefs.data(), h->coefs.size() * sizeof(double));
+  if (b) memcpy(b, h->b.data(), h->b.size() * sizeof(double));
+}
+long long hs_num_cols(void *p) { return ((Harness *)p)->maps.num_cols; }
+long long hs_get_map(void *p, const char *name, int *out)
+{
+  Harness *h = (Harness *)p; const std::vector<int> *v = nullptr;
+  if (!strcmp(name, "external_index")) v = &h->maps.external_index;
+  else if (!strcmp(name, "external_local_index")) v = &h->maps.external_local_index;
+  else if (!strcmp(name, "elements_to_send")) v = &h->maps.elements_to_send;
+  else if (!strcmp(name, "neighbors")) v = &h->maps.neighbors;
+  else if (!strcmp(name, "recv_length")) v = &h->maps.recv_length;
+  else if (!strcmp(name, "send_length")) v = &h->maps.send_length;
+  else return -1;
+  if (out && !v->empty()) memcpy(out, v->data(), v->size() * sizeof(int));
+  return (long long)v->size();
+}
+
+void hs_element(int nx, int ny, int nz, int ex, int ey, int ez, double *K36, double *f8)
+{
+  double grad[192], psi[64];
+  hex8_tables(grad, psi);
+  hex8_element(grad, psi, (double)ex / (double)nx, (double)ey / (double)ny, (double)ez / (double)nz,
+               1.0 / (double)nx, 1.0 / (double)ny, 1.0 / (double)nz, K36, f8);
+}
+void hs_tables(double *grad192, double *psi64) { hex8_tables(grad192, psi64); }
+
+// The exact-dot pipeline (k_chunk_sums -> k_chunk_prefix -> k_dot_maps -> k_dot_walk) executed sequentially with
+// the same per-thread arithmetic.  stats[0] = dirty leaves, stats[1] = 1 if the whole-vector replay path ran,
+// stats[2] = pieces whose collapsed map failed its check.
+double hs_exact_dot(long long n, const double *x, const double *y, long long *stats)
+{
+  const int nchunks = (int)((n + DOT_CHUNK - 1) / DOT_CHUNK);
+  std::vector<double> chunk_sums(nchunks + 1, 0.0), chunk_prefix(nchunks + 2, 0.0);
+  for (int c = 0; c < nchunks; ++c) {      // k_chunk_sums: thread t strides the chunk, warp tree, 8 warp partials
+    double tacc[DOT_CTA_THREADS];
+    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
+      double acc = 0.0;
+      for (int it = 0; it < DOT_LEAF; ++it) { const long long i = (long long)c * DOT_CHUNK + (long long)it * DOT_CTA_THREADS + t; if (i < n) acc += x[i] * y[i]; }
+      tacc[t] = acc;
+    }
+    double tot = 0.0;
+    for (int w = 0; w < DOT_CTA_THREADS / 32; ++w) {
+      double v[32];
+      for (int l = 0; l < 32; ++l) v[l] = tacc[w * 32 + l];
+      for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < 32; ++l) v[l] += (l + o < 32) ? v[l + o] : 0.0;   // shfl_down tree (lane 0 exact)
+      tot += v[0];
+    }
+    chunk_sums[c] = tot;
+  }
+  { double pre = 0.0; for (int c = 0; c < nchunks; ++c) { chunk_prefix[c] = pre; pre += chunk_sums[c]; } chunk_prefix[nchunks] = pre; }
+
+  std::vector<DotMap> cta_maps(nchunks + 1), leaf_maps((size_t)(nchunks + 1) * DOT_CTA_THREADS);
+  std::vector<int> dirty_list;
+  long long dirty_count = 0;
+  for (int c = 0; c < nchunks; ++c) {      // k_dot_maps
+    const long long base = (long long)c * DOT_CHUNK;
+    double prod[DOT_CTA_THREADS][DOT_LEAF], ls[DOT_CTA_THREADS];
+    int cnt[DOT_CTA_THREADS], hyps[DOT_CTA_THREADS + 1];
+    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
+      const long long lb = base + (long long)t * DOT_LEAF;
+      cnt[t] = (int)(lb >= n ? 0 : (n - lb < DOT_LEAF ? n - lb : DOT_LEAF));
+      double s = 0.0;
+      for (int i = 0; i < DOT_LEAF; ++i) { prod[t][i] = lb + i < n ? x[lb + i] * y[lb + i] : 0.0; s += prod[t][i]; }
+      ls[t] = s;
+    }
+    // block scan as in the kernel: warp-inclusive (Hillis-Steele), then sequential warp offsets
+    double inc[DOT_CTA_THREADS], wtot[DOT_CTA_THREADS / 32];
+    for (int w = 0; w < DOT_CTA_THREADS / 32; ++w) {
+      double v[32];
+      for (int l = 0; l < 32; ++l) v[l] = ls[w * 32 + l];
+      for (int o = 1; o < 32; o <<= 1) { double u[32]; for (int l = 0; l < 32; ++l) u[l] = l >= o ? v[l - o] : 0.0; for (int l = 0; l < 32; ++l) if (l >= o) v[l] += u[l]; }
+      for (int l = 0; l < 32; ++l) inc[w * 32 + l] = v[l];
+      wtot[w] = v[31];
+    }
+    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
+      double woff = 0.0;
+      for (int q = 0; q < t / 32; ++q) woff += wtot[q];
+      const double pre = chunk_prefix[c] + (woff + (inc[t] - ls[t]));
+      hyps[t] = dot_hyp_of(pre);
+    }
+    hyps[DOT_CTA_THREADS] = dot_hyp_of(chunk_prefix[c + 1]);
+    DotMap lm[DOT_CTA_THREADS]; bool any = false; bool dl[DOT_CTA_THREADS];
+    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
+      lm[t] = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
+      dl[t] = cnt[t] > 0 && (lm[t].hyp == HYP_INVALID || hyps[t] != hyps[t + 1]);
+      any = any || dl[t];
+    }
+    if (any) {
+      for (int t = 0; t < DOT_CTA_THREADS; ++t) {
+        leaf_maps[(size_t)c * DOT_CTA_THREADS + t] = lm[t];
+        if (dl[t]) { if (dirty_count < DOT_MAX_DIRTY) dirty_list.push_back(c * DOT_CTA_THREADS + t); ++dirty_count; }
+      }
+      cta_maps[c] = dot_invalid();
+    } else {
+      DotMap cm = dot_identity();
+      for (int t = 0; t < DOT_CTA_THREADS; ++t) cm = dot_compose(cm, lm[t]);
+      cta_maps[c] = cm;
+    }
+  }
+  if (stats) { stats[0] = dirty_count; stats[1] = 0; stats[2] = 0; }
+  if (dirty_count > DOT_MAX_DIRTY) { if (stats) stats[1] = 1; return dot_replay(x, y, 0, n, 0.0); }
+  // k_dot_walk
+  const int D = (int)dirty_count, nleaves = nchunks * DOT_CTA_THREADS;
+  std::vector<int> sorted(dirty_list);
+  std::sort(sorted.begin(), sorted.end());
+  std::vector<WalkPiece> pieces(3 * (D + 1));
+  std::vector<DotMap> pmaps(3 * (D + 1));
+  for (int g = 0; g <= D; ++g) dot_gap_pieces(g, D, sorted.data(), nleaves, &pieces[3 * g]);
+  DotWork w{};
+  w.cta_maps = cta_maps.data(); w.leaf_maps = leaf_maps.data();
+  for (size_t pi = 0; pi < pieces.size(); ++pi) {
+    DotMap mm = dot_identity();
+    for (int i = pieces[pi].begin; i < pieces[pi].end; ++i) mm = dot_compose(mm, pieces[pi].kind == 0 ? leaf_maps[i] : cta_maps[i]);
+    pmaps[pi] = mm;
+    if (stats && pieces[pi].end > pieces[pi].begin && mm.hyp == HYP_INVALID) stats[2]++;
+  }
+  return dot_walk_final(D, sorted.data(), pieces.data(), pmaps.data(), w, x, y, n);
+}
+
+double hs_serial_dot(long long n, const double *x, const double *y) { return dot_replay(x, y, 0, n, 0.0); }
+
+}  // extern "C"
