@@ -65,7 +65,8 @@ int mfe_make_local_matrix(mfe_ctx *ctx, int64_t *num_cols);
 /* ref/src/cg_solve.hpp:69-229 with matvec_std (SparseMatrix_functions.hpp:546-578).
  * x_host: in = initial guess, out = solution (nrows doubles; NULL: use/keep the device-resident x).
  * normr_hist (NULL or max_iter+1 doubles): hist[0] = initial residual norm, hist[k] = the norm the reference
- * would print for iteration k.  Returns 0, or 1 on numerical breakdown (cg_solve.hpp:186-198). */
+ * would print for iteration k.  Returns 0, 1 on error, 2 on numerical breakdown (cg_solve.hpp:186-198:
+ * the solve stops there, timers and outputs are still filled). */
 int mfe_cg_solve(mfe_ctx *ctx, double *x_host, int max_iter, double tolerance, int *num_iters, double *normr,
                  double cg_times[MFE_NUM_TIMERS], double *normr_hist, double *rtrans_hist, double *pap_hist,
                  double *alpha_hist);

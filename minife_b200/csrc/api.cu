@@ -706,7 +706,7 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
     }
     if (h.status == CG_BREAKDOWN) {
       fprintf(stderr, "miniFE::cg_solve ERROR, numerical breakdown!\n");
-      rc = 1;
+      rc = 2;
       break;
     }
     if (h.status == CG_CONVERGED || h.stop_iter < k) break;

@@ -1,0 +1,292 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (ctypes wrapper minife_b200), against the
+CPU oracle on the same inputs.  Bars (BASELINE.json north_star): CSR structure and index maps bit-exact; assembled
+values <= 1e-12 relative (we get bit-exact); CG residual history <= 1e-8 relative at the same iteration count (we
+get bit-exact, because matvec / waxpby / dot reproduce the reference's rounding sequence)."""
+import numpy as np
+import pytest
+
+import minife_b200 as mf
+from oracle_lib import Oracle, EPS
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.int64)
+
+
+def assert_bits(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, what
+    same = bits(a) == bits(b)
+    if not same.all():
+        i = int(np.argmin(same))
+        raise AssertionError("%s: %d of %d differ, first at %d: %r vs %r" % (what, (~same).sum(), same.size, i, a.flat[i], b.flat[i]))
+
+
+class Problem:
+    """One rank of an nx*ny*nz problem on cuda:0 through the reference-shaped API."""
+
+    def __init__(self, nx, ny, nz, nranks=1, rank=0):
+        self.gbox = mf.Box([0, nx, 0, ny, 0, nz])
+        self.boxes = mf.box_partition(0, nranks, 2, self.gbox)
+        self.mesh = mf.simple_mesh_description(self.gbox, self.boxes[rank], rank=rank, nranks=nranks, all_boxes=self.boxes)
+        self.A = mf.CSRMatrix()
+        self.b = None
+
+    def structure(self):
+        assert mf.generate_matrix_structure(self.mesh, self.A) == 0
+        n = self.A.num_rows()
+        self.b = mf.Vector(int(self.A.rows[0]), n)
+        self.x = mf.Vector(int(self.A.rows[0]), n)
+        return self
+
+    def assemble(self):
+        mf.assemble_FE_data(self.mesh, self.A, self.b, mf.Parameters())
+        return self
+
+    def bc(self):
+        mf.impose_dirichlet(0.0, self.A, self.b, bc_rows=0)
+        mf.impose_dirichlet(1.0, self.A, self.b, bc_rows=1)
+        return self
+
+    def local(self):
+        mf.make_local_matrix(self.A)
+        return self
+
+    def setup(self):
+        return self.structure().assemble().bc().local()
+
+
+SIZES = [(1, 1, 2), (2, 2, 2), (4, 4, 4), (5, 3, 7), (17, 3, 5), (20, 30, 40), (32, 32, 32), (70, 9, 33)]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_phases_single_rank(n, oracle_built, product_lib):
+    o = Oracle(*n)
+    p = Problem(*n)
+    o.generate_matrix_structure(); p.structure()
+    rows, ro, cols, coefs = o.csr()
+    assert np.array_equal(p.A.rows, rows)
+    assert np.array_equal(p.A.row_offsets, ro)
+    assert np.array_equal(p.A.row_offsets64, ro.astype(np.int64))
+    assert np.array_equal(p.A.packed_cols, cols)
+    assert_bits(p.A.packed_coefs, coefs, "zero coefs")
+    o.assemble_FE_data(); p.assemble()
+    assert_bits(p.A.packed_coefs, o.csr()[3], "A_prebc")
+    assert_bits(p.b.coefs, o.b(), "b_prebc")
+    o.impose_dirichlet(0); mf.impose_dirichlet(0.0, p.A, p.b, bc_rows=0)
+    assert_bits(p.A.packed_coefs, o.csr()[3], "A after bc0")
+    assert_bits(p.b.coefs, o.b(), "b after bc0")
+    o.impose_dirichlet(1); mf.impose_dirichlet(1.0, p.A, p.b, bc_rows=1)
+    assert_bits(p.A.packed_coefs, o.csr()[3], "A")
+    assert_bits(p.b.coefs, o.b(), "b")
+    o.make_local_matrix(); p.local()
+    assert p.A.num_cols == o.num_cols()
+    assert np.array_equal(p.A.packed_cols, o.csr()[2])
+
+
+@pytest.mark.parametrize("n,npr", [((2, 2, 2), 2), ((2, 2, 2), 8), ((8, 8, 8), 8), ((6, 6, 6), 4), ((5, 3, 7), 3), ((12, 10, 9), 5), ((24, 24, 24), 8)])
+def test_phases_every_rank_of_a_partition(n, npr, oracle_built, product_lib):
+    """Each rank's view is built on cuda:0 in turn (no communication is needed before the solve)."""
+    o = Oracle(*n, npr).setup()
+    op = Oracle(*n, npr); op.generate_matrix_structure(); op.assemble_FE_data()
+    for r in range(npr):
+        p = Problem(*n, nranks=npr, rank=r).structure()
+        srows, sro, scols, _ = op.csr(r)
+        assert np.array_equal(p.A.rows, srows) and np.array_equal(p.A.row_offsets, sro), (r, "structure")
+        og = Oracle(*n, npr); og.generate_matrix_structure()
+        assert np.array_equal(p.A.packed_cols, og.csr(r)[2]), (r, "global cols")
+        p.assemble()
+        assert_bits(p.A.packed_coefs, op.csr(r)[3], "rank %d A_prebc" % r)
+        assert_bits(p.b.coefs, op.b(r), "rank %d b_prebc" % r)
+        p.bc().local()
+        rows, ro, cols, coefs = o.csr(r)
+        assert_bits(p.A.packed_coefs, coefs, "rank %d A" % r)
+        assert_bits(p.b.coefs, o.b(r), "rank %d b" % r)
+        assert np.array_equal(p.A.packed_cols, cols), (r, "local cols")
+        assert p.A.num_cols == o.num_cols(r)
+        for m in ("external_index", "external_local_index", "elements_to_send", "neighbors", "recv_length", "send_length"):
+            assert np.array_equal(getattr(p.A, m), o.get_map(m, r)), (r, m)
+        p.mesh.close()
+
+
+@pytest.mark.parametrize("n", [(4, 4, 4), (17, 3, 5), (20, 30, 40), (48, 48, 48)])
+def test_matvec_bit_exact(n, oracle_built, product_lib):
+    o = Oracle(*n).setup()
+    p = Problem(*n).setup()
+    rng = np.random.default_rng(7)
+    for trial in range(3):
+        x = rng.standard_normal(o.nrows()) * 10.0 ** rng.integers(-3, 4, o.nrows())
+        y = np.full(o.nrows(), 123.0)
+        mf.matvec(p.A, x, y)
+        assert_bits(y, o.matvec(x), "matvec trial %d" % trial)
+
+
+def test_matvec_imported_csr_ragged(product_lib):
+    """Hand matrix with ragged rows, empty rows and a row longer than a stencil row (general CSR path)."""
+    rng = np.random.default_rng(3)
+    nrows, ncols = 1000, 1200
+    lens = rng.integers(0, 40, nrows)
+    lens[5] = 0; lens[17] = 2000; lens[500] = 1800; lens[999] = 0
+    ro = np.zeros(nrows + 1, np.int32); ro[1:] = np.cumsum(lens)
+    cols = rng.integers(0, ncols, ro[-1]).astype(np.int32)
+    coefs = rng.standard_normal(ro[-1])
+    x = rng.standard_normal(ncols)
+    p = Problem(10, 10, 9)       # any context; its CSR is replaced
+    mf.lib().mfe_import_csr(p.mesh._h, nrows, ncols, ro, cols, coefs)
+    y = np.zeros(nrows)
+    assert mf.lib().mfe_matvec(p.mesh._h, x, y) == 0, mf.lib().mfe_last_error()
+    ref = np.zeros(nrows)
+    for r in range(nrows):
+        s = 0.0
+        for i in range(ro[r], ro[r + 1]):
+            s = s + coefs[i] * x[cols[i]]
+        ref[r] = s
+    assert_bits(y, ref, "ragged matvec")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 255, 4096, 100003])
+def test_waxpby_bit_exact(n, oracle_built, product_lib):
+    p = Problem(2, 2, 2)
+    rng = np.random.default_rng(n)
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    for a, b in ((1.0, 0.0), (1.0, -1.0), (1.0, 0.3712), (-2.5e-3, 1.0), (0.1, 0.7)):
+        w = np.zeros(n)
+        mf.waxpby(a, x, b, y, w, ctx=p.mesh)
+        assert_bits(w, Oracle.waxpby(a, x, b, y), "waxpby %g %g" % (a, b))
+
+
+DOT_CASES = {
+    "uniform_sq": lambda r, n: (lambda x: (x, x))(r.random(n)),
+    "mostly_positive": lambda r, n: (r.random(n), r.random(n) - 0.02),
+    "ones": lambda r, n: (np.ones(n), np.ones(n)),
+    "ties": lambda r, n: (lambda x: (x, x))(r.integers(0, 4, n) * 0.5),
+    "leading_zeros": lambda r, n: (lambda x: (x, x))(np.concatenate([np.zeros(n // 2), r.random(n - n // 2)])),
+    "all_zero": lambda r, n: (np.zeros(n), np.zeros(n)),
+    "wide_range": lambda r, n: (lambda x: (x, x))(np.abs(r.standard_normal(n)) * 10.0 ** r.integers(-8, 8, n)),
+    "negative_sum": lambda r, n: (-r.random(n), r.random(n)),
+    "mixed_sign": lambda r, n: (r.standard_normal(n), r.standard_normal(n)),      # whole-vector replay path
+    "with_inf": lambda r, n: (lambda x: (x, x))(np.where(np.arange(n) == n // 3, np.inf, r.random(n))),
+}
+
+
+@pytest.mark.parametrize("case", sorted(DOT_CASES))
+@pytest.mark.parametrize("n", [1, 17, 4095, 4097, 70001, 1234567])
+def test_dot_reproduces_serial_sum(case, n, oracle_built, product_lib):
+    p = Problem(2, 2, 2)
+    x, y = DOT_CASES[case](np.random.default_rng(n), n)
+    x, y = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)
+    want = Oracle.dot(x, y)
+    got = mf.dot(x, y, ctx=p.mesh)
+    assert bits(np.array([got]))[0] == bits(np.array([want]))[0] or (np.isnan(got) and np.isnan(want)), (got, want)
+    p.mesh.set_dot_mode(mf.DOT_SERIAL)
+    got = mf.dot(x, y, ctx=p.mesh)
+    assert bits(np.array([got]))[0] == bits(np.array([want]))[0] or (np.isnan(got) and np.isnan(want)), ("serial", got, want)
+    p.mesh.set_dot_mode(mf.DOT_TREE)
+    got = mf.dot(x, y, ctx=p.mesh)
+    if np.isfinite(want):
+        assert abs(got - want) <= 1e-9 * np.abs(x * y).sum() + 1e-300, ("tree", got, want)
+
+
+@pytest.mark.parametrize("n", [(1, 1, 2), (4, 4, 4), (17, 3, 5), (20, 30, 40), (32, 32, 32), (64, 64, 64)])
+def test_cg_history_bit_exact(n, oracle_built, product_lib):
+    """Free-running CG: same iteration count, bit-identical residual / p.Ap / alpha history and solution
+    (tolerance demanded by BASELINE.json: 1e-8 relative)."""
+    o = Oracle(*n).setup()
+    want = o.cg_solve(200, EPS)
+    p = Problem(*n).setup()
+    iters, normr, times, h = mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS, history=True)
+    assert iters == want["num_iters"], (iters, want["num_iters"])
+    assert_bits(h["normr"], want["normr"], "normr history")
+    assert_bits(h["pap"][1:], want["pap"][1:], "p.Ap history")
+    assert_bits(h["alpha"][1:], want["alpha"][1:], "alpha history")
+    assert_bits([normr], [want["final_normr"]], "final normr")
+    assert_bits(p.x.coefs, o.x(), "solution x")
+    rel = np.abs(h["normr"] - want["normr"]) / want["normr"].clip(1e-300)
+    assert rel.max() <= 1e-8
+    assert times[mf.TOTAL] > 0 and times[mf.MATVEC] > 0
+
+
+def test_cg_32_stops_at_106_like_the_reference(oracle_built, product_lib):
+    """tol = eps on the absolute residual stops 32^3 after 106 iterations (1.2517e-16)."""
+    p = Problem(32, 32, 32).setup()
+    iters, normr, _ = mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS)
+    assert iters == 106
+    assert abs(normr - 1.2517e-16) < 1e-20
+
+
+def test_cg_dot_modes(oracle_built, product_lib):
+    """MFE_DOT_SERIAL is bit-identical too; MFE_DOT_TREE is not reproducible but converges."""
+    n = (24, 24, 24)
+    want = Oracle(*n).setup().cg_solve(200, EPS)
+    p = Problem(*n).setup()
+    p.mesh.set_dot_mode(mf.DOT_SERIAL)
+    iters, normr, _, h = mf.cg_solve(p.A, p.b, p.x, None, 200, EPS, history=True)
+    assert iters == want["num_iters"]
+    assert_bits(h["normr"], want["normr"], "serial-dot history")
+    p.mesh.set_dot_mode(mf.DOT_TREE)
+    p.x.coefs[:] = 0
+    iters, normr, _ = mf.cg_solve(p.A, p.b, p.x, None, 200, EPS)
+    assert abs(iters - want["num_iters"]) <= 3 and normr < 1e-14
+
+
+def test_cg_max_iter_and_tolerance_semantics(oracle_built, product_lib):
+    n = (12, 12, 12)
+    for max_iter, tol in ((0, EPS), (1, EPS), (5, EPS), (200, 1e-3), (200, 1e9)):
+        o = Oracle(*n).setup()
+        want = o.cg_solve(max_iter, tol)
+        p = Problem(*n).setup()
+        iters, normr, _ = mf.cg_solve(p.A, p.b, p.x, None, max_iter, tol)
+        assert iters == want["num_iters"], (max_iter, tol)
+        assert_bits([normr], [want["final_normr"]], "normr %s %s" % (max_iter, tol))
+        assert_bits(p.x.coefs, o.x(), "x %s %s" % (max_iter, tol))
+
+
+def test_cg_nonzero_initial_guess(oracle_built, product_lib):
+    n = (10, 11, 12)
+    o = Oracle(*n).setup()
+    x0 = np.random.default_rng(5).random(o.nrows())
+    o.L.mfo_set_x(o.h, 0, x0)
+    want = o.cg_solve(50, EPS)
+    p = Problem(*n).setup()
+    p.x.coefs[:] = x0
+    iters, normr, _, h = mf.cg_solve(p.A, p.b, p.x, None, 50, EPS, history=True)
+    assert iters == want["num_iters"]
+    assert_bits(h["normr"], want["normr"], "history")
+    assert_bits(p.x.coefs, o.x(), "x")
+
+
+def test_errors_are_loud(product_lib):
+    p = Problem(4, 4, 4).structure()
+    with pytest.raises(mf.LibraryError):
+        mf.cg_solve(p.A, p.b, p.x)          # make_local_matrix not called (cg_solve.hpp:99-104)
+    p.assemble().bc().local()
+    with pytest.raises(mf.LibraryError):
+        mf.impose_dirichlet(0.0, p.A, p.b, bc_rows=0)    # columns are local now
+
+
+def test_size_independent_properties_128(product_lib):
+    """At a size the oracle does not finish in seconds: structure counts, symmetry-free invariants, and the
+    dot-mode cross-check (exact == serial bits) on real CG vectors."""
+    n = 128
+    p = Problem(n, n, n).setup()
+    N = (n + 1) ** 3
+    assert p.A.num_rows() == N and p.A.num_nonzeros() == (3 * (n + 1) - 2) ** 3
+    ro = p.A.row_offsets64
+    lens = np.diff(ro)
+    assert lens.min() == 8 and lens.max() == 27 and ro[-1] == p.A.num_nonzeros()
+    coefs, cols = p.A.packed_coefs, p.A.packed_cols
+    # interior rows sum to ~0 (constant vector in the null space of the diffusion operator before BCs touch them)
+    ones = np.ones(N); y = np.zeros(N)
+    mf.matvec(p.A, ones, y)
+    idx = np.arange(N); ix, iy, iz = idx % (n + 1), (idx // (n + 1)) % (n + 1), idx // (n + 1) ** 2
+    interior = (ix > 1) & (ix < n - 1) & (iy > 1) & (iy < n - 1) & (iz > 1) & (iz < n - 1)
+    assert np.abs(y[interior]).max() < 1e-12
+    bc = (ix == 0) | (iy == 0) | (iz == 0) | (ix == n) | (iy == n) | (iz == n)
+    assert np.array_equal(y[bc], np.ones(bc.sum()))          # identity rows
+    iters, normr, _, h = mf.cg_solve(p.A, p.b, p.x, None, 200, EPS, history=True)
+    assert iters == 200
+    # golden values of the reference at 128^3 (printed with 6 digits)
+    assert abs(h["normr"][0] - 129.004) < 5e-4 and abs(h["normr"][20] - 0.0529612) < 5e-8
+    assert abs(h["normr"][100] - 0.0036414) < 5e-8 and abs(normr - 1.13069e-05) < 5e-11
