@@ -265,15 +265,18 @@ def main():
         wall = time.perf_counter() - t0
         return it.value, nr.value, times, wall
 
+    op_s = []
+
     def timed(host_buffers, steps):
         dev_s, wall_s, mv_s, its, last = [], [], [], [], None
         for _ in range(steps):
             it, nr, times, wall = solve(host_buffers)
             # device time of the solve: CUDA events on the library stream (cg_times[TOTAL]); max over ranks
-            tt = torch.tensor([times[4], wall, times[2]], dtype=torch.float64, device="cuda")
+            tt = torch.tensor([times[4], wall, times[2], times[0], times[1]], dtype=torch.float64, device="cuda")
             if dist:
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dev_s.append(float(tt[0])); wall_s.append(float(tt[1])); mv_s.append(float(tt[2])); its.append(it); last = nr
+            op_s.append((float(tt[3]), float(tt[4])))
         return dev_s, wall_s, mv_s, its, last
 
     for _ in range(args.warmup):
@@ -285,6 +288,8 @@ def main():
     dev_s, wall_s, mv_s, its, normr = timed(False, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = mesh.launch_count() - launches0
+    cg_times = {"WAXPY_s": float(np.mean([o[0] for o in op_s])), "DOT_s": float(np.mean([o[1] for o in op_s])),
+                "MATVEC_s": float(np.mean(mv_s)), "TOTAL_s": float(np.mean(dev_s))}
     e_dev, e_wall, _, e_its, _ = timed(True, max(1, min(args.steps, 3)))
 
     iters = its[-1]
@@ -328,7 +333,7 @@ def main():
                        "l2": "inputs larger than L2 (7.4 GB per iteration vs 126 MB)", "dot": ["exact (order-reproducing)", "serial", "tree"][args.dot_mode],
                        "flop_model": "ref/src/driver.hpp:322-341"},
             "hbm_gbs": hbm_gbs, "hbm_gbs_per_gpu": hbm_gbs / world, "pct_of_8TBs_per_gpu": 100.0 * hbm_gbs / world / 8000.0,
-            "ms_per_cg_iteration": t_step * 1e3 / max(iters, 1),
+            "ms_per_cg_iteration": t_step * 1e3 / max(iters, 1), "cg_times": cg_times,
             "setup_ms": {"structure": mesh.phase_ms("structure"), "assembly": mesh.phase_ms("assembly"), "assembly_elem": mesh.phase_ms("assembly_elem"),
                          "assembly_gather": mesh.phase_ms("assembly_gather"), "dirichlet0": mesh.phase_ms("dirichlet0"), "dirichlet1": mesh.phase_ms("dirichlet1"),
                          "make_local": mesh.phase_ms("make_local"), "wall_all": t_setup * 1e3},

@@ -71,6 +71,8 @@ int mfe_cg_solve(mfe_ctx *ctx, double *x_host, int max_iter, double tolerance, i
                  double cg_times[MFE_NUM_TIMERS], double *normr_hist, double *rtrans_hist, double *pap_hist,
                  double *alpha_hist);
 int mfe_set_dot_mode(mfe_ctx *ctx, int mode);
+/* tuning knobs: "matvec_config" = index into the SpMV (rows-per-tile, groups, stages) table */
+int mfe_set_option(mfe_ctx *ctx, const char *name, int64_t value);
 /* 1: record per-op-class CUDA events to fill cg_times[WAXPY,DOT,MATVEC] (default), 0: only TOTAL */
 int mfe_set_op_timing(mfe_ctx *ctx, int enabled);
 

@@ -38,6 +38,7 @@ SIGNATURES = {
     "mfe_cg_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp]),
     "mfe_set_dot_mode": (C.c_int, [_vp, C.c_int]),
     "mfe_set_op_timing": (C.c_int, [_vp, C.c_int]),
+    "mfe_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),
     "mfe_matvec": (C.c_int, [_vp, _f64p, _f64p]),
     "mfe_waxpby": (C.c_int, [_vp, _i64, C.c_double, _f64p, C.c_double, _f64p, _f64p]),
     "mfe_dot": (C.c_int, [_vp, _i64, _f64p, _f64p, C.POINTER(C.c_double)]),

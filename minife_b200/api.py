@@ -99,6 +99,9 @@ class simple_mesh_description:
     def set_dot_mode(self, mode):
         check(lib().mfe_set_dot_mode(self._h, mode), "mfe_set_dot_mode")
 
+    def set_option(self, name, value):
+        check(lib().mfe_set_option(self._h, name.encode(), int(value)), "mfe_set_option(%s)" % name)
+
     def set_op_timing(self, enabled):
         check(lib().mfe_set_op_timing(self._h, int(enabled)), "mfe_set_op_timing")
 

@@ -78,7 +78,7 @@ static int nccl_load()
 // ---------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------
-enum { MV_TR = 64 };            // rows per SpMV tile (must divide DOT_CHUNK)
+enum { MV_TR_MAX = 128 };       // largest rows-per-tile of any SpMV configuration (tile rows must divide DOT_CHUNK)
 
 struct DotWs {                  // workspace of one exact dot (sized for nrows)
   DotWork w{};
@@ -123,6 +123,8 @@ struct mfe_ctx {
   double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
   int dot_mode = MFE_DOT_EXACT;
   int op_timing = 1;
+  int mv_cfg = 0;                // SpMV configuration (see matvec_configs)
+  int tr = 64;                   // rows per SpMV tile of that configuration
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -318,7 +320,7 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
   }
   free_dev(ob); free_dev(ox);
   const int64_t nchunks = (need + DOT_CHUNK - 1) / DOT_CHUNK;
-  const int64_t ntiles = (need + MV_TR - 1) / MV_TR;
+  const int64_t ntiles = (need + 31) / 32;
   if (dev_alloc(&c->d_tile_sums, ntiles + 1) || dev_alloc(&c->dot.w.chunk_sums, nchunks + 1) || dev_alloc(&c->dot.w.chunk_prefix, nchunks + 2) ||
       dev_alloc(&c->dot.w.cta_maps, nchunks + 1) || dev_alloc(&c->dot.w.leaf_maps, (nchunks + 1) * DOT_CTA_THREADS) ||
       dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) || dev_alloc(&c->dot.w.result, 1) ||
@@ -340,11 +342,11 @@ struct PhaseTimer {
 
 static int build_tile_base(mfe_ctx *c)
 {
-  c->ntiles = (c->nrows + MV_TR - 1) / MV_TR;
+  c->ntiles = (c->nrows + c->tr - 1) / c->tr;
   free_dev(c->d_tile_base);
   if (dev_alloc(&c->d_tile_base, c->ntiles + 2)) return 1;
-  if (c->mesh_csr) k_tile_base_mesh<<<grid_for(c->ntiles + 1, 256), 256, 0, c->stream>>>(c->m, MV_TR, c->ntiles, c->d_tile_base);
-  else k_tile_base_csr<<<grid_for(c->ntiles + 1, 256), 256, 0, c->stream>>>(c->d_roff, c->nrows, MV_TR, c->ntiles, c->d_tile_base);
+  if (c->mesh_csr) k_tile_base_mesh<<<grid_for(c->ntiles + 1, 256), 256, 0, c->stream>>>(c->m, c->tr, c->ntiles, c->d_tile_base);
+  else k_tile_base_csr<<<grid_for(c->ntiles + 1, 256), 256, 0, c->stream>>>(c->d_roff, c->nrows, c->tr, c->ntiles, c->d_tile_base);
   c->launches++;
   CK(cudaGetLastError());
   return 0;
@@ -412,7 +414,7 @@ extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
     if (ne > 0) { k_elements<<<grid_for(ne, 128), 128, 0, c->stream>>>(m, sl, KF); c->launches++; }
     cudaEventRecord(e1, c->stream);
     const int64_t nr = (int64_t)m.lnx * m.lny * (iz1 - iz0);
-    k_gather_rows<<<grid_for(nr, 128), 128, 0, c->stream>>>(m, sl, KF, iz0, iz1, c->d_roff, c->d_tile_base, MV_TR, c->d_coefs, c->d_b);
+    k_gather_rows<<<grid_for(nr, 128), 128, 0, c->stream>>>(m, sl, KF, iz0, iz1, c->d_roff, c->d_tile_base, c->tr, c->d_coefs, c->d_b);
     c->launches++;
     cudaEventRecord(e2, c->stream);
     cudaEventSynchronize(e2);
@@ -434,7 +436,7 @@ extern "C" int mfe_impose_dirichlet(mfe_ctx *c, double val, int which)
   if (which != 0 && which != 1) return fail("mfe_impose_dirichlet: which_set must be 0 or 1");
   CK(cudaSetDevice(c->device));
   PhaseTimer tm(c->stream);
-  k_dirichlet<<<grid_for(c->nrows, 128), 128, 0, c->stream>>>(c->m, which, val, c->d_roff, c->d_tile_base, MV_TR, c->d_cols, c->d_coefs, c->d_b);
+  k_dirichlet<<<grid_for(c->nrows, 128), 128, 0, c->stream>>>(c->m, which, val, c->d_roff, c->d_tile_base, c->tr, c->d_cols, c->d_coefs, c->d_b);
   c->launches++;
   (which == 0 ? c->t_dir0 : c->t_dir1) = tm.stop();
   CK(cudaGetLastError());
@@ -537,11 +539,32 @@ static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
   return 0;
 }
 
+// SpMV configurations: rows per tile (= threads per group), groups per CTA, smem stages per group
+struct MvCfg { int tr, g, s; };
+static const MvCfg matvec_configs[] = { {64, 4, 2}, {64, 3, 3}, {32, 8, 2}, {128, 2, 2}, {64, 5, 2}, {32, 6, 3}, {32, 4, 5}, {64, 2, 4}, {128, 1, 4}, {32, 10, 2} };
+enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
+
+static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, double *sums, const CgScalars *gate, int k)
+{
+  switch (c->mv_cfg) {
+    case 0: return launch_matvec_cfg<64, 4, 2>(c, x, y, sums, gate, k);
+    case 1: return launch_matvec_cfg<64, 3, 3>(c, x, y, sums, gate, k);
+    case 2: return launch_matvec_cfg<32, 8, 2>(c, x, y, sums, gate, k);
+    case 3: return launch_matvec_cfg<128, 2, 2>(c, x, y, sums, gate, k);
+    case 4: return launch_matvec_cfg<64, 5, 2>(c, x, y, sums, gate, k);
+    case 5: return launch_matvec_cfg<32, 6, 3>(c, x, y, sums, gate, k);
+    case 6: return launch_matvec_cfg<32, 4, 5>(c, x, y, sums, gate, k);
+    case 7: return launch_matvec_cfg<64, 2, 4>(c, x, y, sums, gate, k);
+    case 8: return launch_matvec_cfg<128, 1, 4>(c, x, y, sums, gate, k);
+    case 9: return launch_matvec_cfg<32, 10, 2>(c, x, y, sums, gate, k);
+  }
+  return fail("bad matvec configuration %d", c->mv_cfg);
+}
+
 static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k)
 {
   if (exchange(c, x, gate, k)) return 1;
-  if (launch_matvec_cfg<MV_TR, 4, 2>(c, x, y, with_sums ? c->d_tile_sums : nullptr, gate, k)) return 1;
-  return 0;
+  return launch_matvec_local(c, x, y, with_sums ? c->d_tile_sums : nullptr, gate, k);
 }
 
 static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, ScalarArg b, const double *y, double *w, const CgScalars *gate, int k)
@@ -569,7 +592,7 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
     c->launches++;
   } else {
     if (sums_kind == 0) { if (nchunks > 0) { k_chunk_sums<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w.chunk_sums, gate, k); c->launches++; } }
-    if (sums_kind == 2) k_chunk_prefix<<<1, 1024, 0, c->stream>>>(c->d_tile_sums, DOT_CHUNK / MV_TR, (n + MV_TR - 1) / MV_TR, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
+    if (sums_kind == 2) k_chunk_prefix<<<1, 1024, 0, c->stream>>>(c->d_tile_sums, DOT_CHUNK / c->tr, (n + c->tr - 1) / c->tr, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
     else k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, 1, nchunks, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
     c->launches++;
     if (c->dot_mode == MFE_DOT_TREE) {
@@ -744,6 +767,22 @@ extern "C" int mfe_set_dot_mode(mfe_ctx *c, int mode)
 }
 extern "C" int mfe_set_op_timing(mfe_ctx *c, int on) { if (!c) return fail("null context"); c->op_timing = on; return 0; }
 
+extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
+{
+  if (!c || !name) return fail("mfe_set_option: bad arguments");
+  if (!strcmp(name, "matvec_config")) {
+    if (value < 0 || value >= N_MV_CFG) return fail("mfe_set_option: matvec_config must be in [0,%d)", (int)N_MV_CFG);
+    CK(cudaSetDevice(c->device));
+    c->mv_cfg = (int)value;
+    if (c->tr != matvec_configs[value].tr) {
+      c->tr = matvec_configs[value].tr;
+      if (c->has_structure) { CK(cudaStreamSynchronize(c->stream)); if (build_tile_base(c)) return 1; CK(cudaStreamSynchronize(c->stream)); }
+    }
+    return 0;
+  }
+  return fail("mfe_set_option: unknown option '%s'", name);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer kernel entry points
 // ---------------------------------------------------------------------------------------------------------
@@ -843,8 +882,8 @@ extern "C" int mfe_export_csr(mfe_ctx *c, int *rows, int *row_offsets, int64_t *
     CK(cudaMemcpy(lo.data(), c->d_roff, (c->nrows + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(tb.data(), c->d_tile_base, (c->ntiles + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost));
     for (int64_t r = 0; r <= c->nrows; ++r) {
-      const int64_t t = std::min(r / MV_TR, c->ntiles - 1);
-      row_offsets64[r] = tb[t] + (int64_t)(uint32_t)(lo[r] - lo[t * MV_TR]);
+      const int64_t t = std::min(r / c->tr, c->ntiles - 1);
+      row_offsets64[r] = tb[t] + (int64_t)(uint32_t)(lo[r] - lo[t * c->tr]);
     }
   }
   if (cols) CK(cudaMemcpy(cols, c->d_cols, c->nnz * sizeof(int), cudaMemcpyDeviceToHost));
@@ -935,9 +974,9 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
   CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   auto body = [&](int rep) -> int {
-    if (!strcmp(what, "matvec")) return launch_matvec_cfg<MV_TR, 4, 2>(c, c->d_p, c->d_Ap, nullptr, nullptr, 0);
-    if (!strcmp(what, "matvec_dot")) return launch_matvec_cfg<MV_TR, 4, 2>(c, c->d_p, c->d_Ap, c->d_tile_sums, nullptr, 0);
-    if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, MV_TR, c->d_p, c->d_Ap, n); c->launches++; return 0; }
+    if (!strcmp(what, "matvec")) return launch_matvec_local(c, c->d_p, c->d_Ap, nullptr, nullptr, 0);
+    if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, c->d_p, c->d_Ap, c->d_tile_sums, nullptr, 0);
+    if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n); c->launches++; return 0; }
     if (!strcmp(what, "waxpby")) { launch_waxpby(c, n, one, c->d_r, half, c->d_p, c->d_tmp1, nullptr, 0); return 0; }
     if (!strcmp(what, "dot_rr")) return launch_dot(c, n, c->d_r, c->d_r, 0, EPI_NONE, 0, false, nullptr);
     if (!strcmp(what, "dot_pap")) return launch_dot(c, n, c->d_Ap, c->d_p, 0, EPI_NONE, 0, false, nullptr);

@@ -39,6 +39,10 @@ __device__ inline void cg_epilogue(CgScalars *s, int epi, int k, double dot, dou
     if (normr_hist) normr_hist[0] = s->normr;
     if (rtrans_hist) rtrans_hist[0] = dot;
     if (!(s->normr > s->tol)) { s->stop_iter = 0; s->status = CG_CONVERGED; }   // loop test, cg_solve.hpp:152
+    else if (s->max_iter >= 1) {               // iteration 1 recomputes normr = sqrt(rtrans) unchanged (cg_solve.hpp:154,163)
+      if (normr_hist) normr_hist[1] = s->normr;
+      if (rtrans_hist) rtrans_hist[1] = dot;
+    }
   } else if (epi == EPI_RR) {                  // cg_solve.hpp:157-163 (k >= 2)
     s->oldrtrans = s->rtrans;
     s->rtrans = dot;
