@@ -123,7 +123,7 @@ struct mfe_ctx {
   double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
   int dot_mode = MFE_DOT_EXACT;
   int op_timing = 1;
-  int mv_cfg = 0;                // SpMV configuration (see matvec_configs)
+  int mv_cfg = 4;                // SpMV configuration (see matvec_configs): 64 rows x 5 groups x 2 stages
   int tr = 64;                   // rows per SpMV tile of that configuration
 
   // comm
@@ -243,6 +243,7 @@ extern "C" mfe_ctx *mfe_create(int rank, int nranks, int device, const int globa
   cudaMemcpyToSymbol(c_grad, grad, sizeof grad);
   cudaMemcpyToSymbol(c_psi, psi, sizeof psi);
   if (dev_alloc(&c->d_sc, 1) || dev_alloc(&c->d_gather, nranks)) { delete c; return nullptr; }
+  cudaFuncSetAttribute(k_dot_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DOT_MAX_DIRTY * DOT_LEAF * sizeof(double)));
   cudaMemset(c->d_sc, 0, sizeof(CgScalars));
   if ((e = cudaGetLastError()) != cudaSuccess) { fail("mfe_create: %s", cudaGetErrorString(e)); delete c; return nullptr; }
   return c;
@@ -507,7 +508,7 @@ template <int TR, int G, int S>
 static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, double *tile_sums, const CgScalars *gate, int k)
 {
   static bool attr_set[64] = { false };
-  const size_t smem = (size_t)G * S * MatvecCfg<TR>::SLOT_BYTES + (size_t)G * S * 8 + (size_t)G * (TR / 32) * 8 + 64;
+  const size_t smem = (size_t)G * S * MatvecCfg<TR>::SLOT_BYTES + (size_t)G * S * 8 + (size_t)G * 2 * (TR / 32) * 8 + 64;
   auto kern = k_matvec<TR, G, S>;
   if (!attr_set[c->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -592,15 +593,18 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
     c->launches++;
   } else {
     if (sums_kind == 0) { if (nchunks > 0) { k_chunk_sums<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w.chunk_sums, gate, k); c->launches++; } }
-    if (sums_kind == 2) k_chunk_prefix<<<1, 1024, 0, c->stream>>>(c->d_tile_sums, DOT_CHUNK / c->tr, (n + c->tr - 1) / c->tr, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
-    else k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, 1, nchunks, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
+    if (sums_kind == 2 && nchunks > 0) {
+      k_tiles_to_chunks<<<grid_for(nchunks, 8), 256, 0, c->stream>>>(c->d_tile_sums, DOT_CHUNK / c->tr, (n + c->tr - 1) / c->tr, nchunks, w.chunk_sums, gate, k);
+      c->launches++;
+    }
+    k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, 1, nchunks, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
     c->launches++;
     if (c->dot_mode == MFE_DOT_TREE) {
       k_dot_tree_finish<<<1, 1, 0, c->stream>>>(w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
       c->launches++;
     } else {
       if (nchunks > 0) { k_dot_maps<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k); c->launches++; }
-      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
+      k_dot_walk<<<1, WALK_THREADS, DOT_MAX_DIRTY * DOT_LEAF * sizeof(double), c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
       c->launches++;
     }
   }

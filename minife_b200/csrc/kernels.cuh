@@ -276,7 +276,7 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   const int group = threadIdx.x / TR, tg = threadIdx.x % TR;
   unsigned char *gbase = smem + (size_t)group * S * SLOT;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + group * S;
-  double *wsum = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + G * S * 8) + group * NW;
+  double *wsum = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + G * S * 8) + group * 2 * NW;   // [2][NW], by tile parity
 
   const int64_t gg = (int64_t)blockIdx.x * G + group, stride = (int64_t)gridDim.x * G;
 
@@ -329,6 +329,8 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     const bool staged = ntile > 0 && ntile <= CAP;
 
     double sum = 0.0, prod = 0.0;     // beta*y with beta = 0 (SparseMatrix_functions.hpp:565-568)
+    const double xr = (tile_sums && r < nrows) ? __ldg(x + r) : 0.0;
+    double *ws = wsum + (j & 1) * NW;
     if (staged) {
       mbar_wait(&bars[s], parity);
       phase_bits ^= 1u << s;
@@ -359,21 +361,21 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     }
     if (r < nrows) {
       y[r] = sum;
-      if (tile_sums) prod = x[r] * sum;
+      prod = xr * sum;
     }
     if (tile_sums) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) prod += __shfl_down_sync(0xffffffffu, prod, o);
-      if ((tg & 31) == 0) wsum[tg >> 5] = prod;
+      if ((tg & 31) == 0) ws[tg >> 5] = prod;
     }
     // every thread of the group is done with stage s -> it can be refilled
     if (TR == 32) __syncwarp(); else group_sync(1 + group, TR);
     if (tg == 0) {
-      if (tile_sums) { double ts = 0.0; for (int w = 0; w < NW; ++w) ts += wsum[w]; tile_sums[t] = ts; }
+      if (tile_sums) { double ts = 0.0; for (int w = 0; w < NW; ++w) ts += ws[w]; tile_sums[t] = ts; }
       const int64_t t2 = t + (int64_t)S * stride;
       if (t2 < ntiles) issue(t2, s);
     }
-    if (tile_sums && TR != 32) group_sync(1 + group, TR);   // wsum is reused by the next tile
+    // ws of this parity is next written two tiles later, i.e. after the next tile's barrier: no extra sync
   }
 }
 
@@ -470,6 +472,20 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_chunk_sums(int64_t n, const
   }
   const double t = block_sum_256(acc, sh);
   if (threadIdx.x == 0) chunk_sums[blockIdx.x] = t;
+}
+
+// SpMV tile sums -> chunk sums (per = DOT_CHUNK / rows-per-tile partial sums per chunk), one warp per chunk
+__global__ void __launch_bounds__(256) k_tiles_to_chunks(const double *__restrict__ tile_sums, int per, int64_t ntiles, int nchunks,
+                                                         double *__restrict__ chunk_sums, const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= nchunks) return;
+  double v = 0.0;
+  for (int q = lane; q < per; q += 32) { const int64_t i = (int64_t)c * per + q; if (i < ntiles) v += tile_sums[i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if (lane == 0) chunk_sums[c] = v;
 }
 
 // Exclusive prefix over chunks: sums[] has `per` consecutive partial sums per chunk (per = 1 for chunk sums,
@@ -618,7 +634,10 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
   __shared__ int sorted[DOT_MAX_DIRTY];
   __shared__ WalkPiece pieces[WALK_MAX_PIECES];
   __shared__ DotMap pmaps[WALK_MAX_PIECES];
-  __shared__ int npieces_sh;
+  __shared__ DotMap wred[WALK_THREADS / 32];
+  __shared__ int big[WALK_MAX_PIECES];
+  __shared__ int nbig_sh;
+  extern __shared__ double replay_prod[];          // [DOT_MAX_DIRTY][DOT_LEAF] products of the dirty leaves
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = *w.dirty_count;
   const int nleaves = nchunks * DOT_CTA_THREADS;
@@ -627,6 +646,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
     if (tid == 0) s = dot_replay(x, y, 0, n, 0.0);
   } else {
     for (int i = tid; i < D; i += WALK_THREADS) dirty[i] = w.dirty_list[i];
+    if (tid == 0) nbig_sh = 0;
     __syncthreads();
     for (int i = tid; i < D; i += WALK_THREADS) {        // rank sort (leaf indices are distinct)
       const int v = dirty[i]; int rk = 0;
@@ -634,14 +654,24 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
       sorted[rk] = v;
     }
     __syncthreads();
+    // products of the dirty leaves, fetched by all threads at once (the sequential walk then reads smem only)
+    for (int q = tid; q < D * DOT_LEAF; q += WALK_THREADS) {
+      const int64_t i = (int64_t)sorted[q / DOT_LEAF] * DOT_LEAF + (q % DOT_LEAF);
+      replay_prod[q] = i < n ? __dmul_rn(x[i], y[i]) : 0.0;
+    }
     // pieces of gap g (between dirty leaf g-1 and dirty leaf g) live at pieces[3g .. 3g+2]
-    for (int g = tid; g <= D; g += WALK_THREADS) dot_gap_pieces(g, D, sorted, nleaves, pieces + 3 * g);
-    if (tid == 0) npieces_sh = 3 * (D + 1);
+    for (int g = tid; g <= D; g += WALK_THREADS) {
+      dot_gap_pieces(g, D, sorted, nleaves, pieces + 3 * g);
+      for (int q = 0; q < 3; ++q)
+        if (pieces[3 * g + q].end - pieces[3 * g + q].begin > 256) big[atomicAdd(&nbig_sh, 1)] = 3 * g + q;
+    }
     __syncthreads();
-    const int npieces = npieces_sh;
+    const int npieces = 3 * (D + 1), nbig = nbig_sh;
+    // small pieces: one warp each, all warps in parallel
     for (int pi = warp; pi < npieces; pi += WALK_THREADS / 32) {
       const WalkPiece pc = pieces[pi];
       const int len = pc.end - pc.begin;
+      if (len > 256) continue;
       DotMap m = dot_identity();
       if (len > 0) {
         const int per = (len + 31) / 32;
@@ -651,8 +681,45 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
       }
       if (lane == 31) pmaps[pi] = m;
     }
+    // big pieces: the whole CTA cooperates on each (contiguous sub-range per thread, warp scan, then warp 0)
+    for (int bi = 0; bi < nbig; ++bi) {
+      const int pi = big[bi];
+      const WalkPiece pc = pieces[pi];
+      const int len = pc.end - pc.begin;
+      const int per = (len + WALK_THREADS - 1) / WALK_THREADS;
+      const int b = pc.begin + tid * per, e = min(pc.end, b + per);
+      DotMap m = dot_identity();
+      for (int i = b; i < e; ++i) m = dot_compose(m, pc.kind == 0 ? w.leaf_maps[i] : w.cta_maps[i]);
+      m = warp_compose(m, lane);
+      if (lane == 31) wred[warp] = m;
+      __syncthreads();
+      if (warp == 0) {
+        DotMap r = wred[lane];
+        r = warp_compose(r, lane);
+        if (lane == 31) pmaps[pi] = r;
+      }
+      __syncthreads();
+    }
     __syncthreads();
-    if (tid == 0) s = dot_walk_final(D, sorted, pieces, pmaps, w, x, y, n);
+    if (tid == 0) {
+      // the sequential walk (dot_walk_final with the dirty leaves replayed from shared memory)
+      for (int g = 0; g <= D; ++g) {
+        for (int q = 0; q < 3; ++q) {
+          const WalkPiece pc = pieces[3 * g + q];
+          if (pc.end <= pc.begin) continue;
+          if (!dot_apply(pmaps[3 * g + q], s)) s = dot_walk_piece_slow(pc, w, x, y, n, s);
+        }
+        if (g < D) {
+          const int64_t b = (int64_t)sorted[g] * DOT_LEAF;
+          const int cnt = (int)(b + DOT_LEAF <= n ? DOT_LEAF : n - b);
+          double pr[DOT_LEAF];
+#pragma unroll
+          for (int i = 0; i < DOT_LEAF; ++i) pr[i] = replay_prod[g * DOT_LEAF + i];
+#pragma unroll
+          for (int i = 0; i < DOT_LEAF; ++i) if (i < cnt) s = __dadd_rn(s, pr[i]);
+        }
+      }
+    }
   }
   if (tid == 0) {
     *w.result = s;
