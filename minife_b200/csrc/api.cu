@@ -125,6 +125,7 @@ struct mfe_ctx {
   int op_timing = 1;
   int mv_cfg = 4;                // SpMV configuration (see matvec_configs): 64 rows x 5 groups x 2 stages
   int tr = 64;                   // rows per SpMV tile of that configuration
+  int mv_flags = MV_STREAM_HINT | MV_PREFETCH;
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -517,7 +518,7 @@ static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, double *til
   const int64_t groups_needed = c->ntiles;
   int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (groups_needed + G - 1) / G));
   kern<<<grid, TR * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded,
-                                          tile_sums, gate, k);
+                                          c->num_cols > 0 ? c->num_cols : c->nrows, c->mv_flags, 0, tile_sums, gate, k);
   c->launches++;
   return 0;
 }
@@ -784,6 +785,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
     }
     return 0;
   }
+  if (!strcmp(name, "matvec_flags")) { c->mv_flags = (int)value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
 

@@ -21,6 +21,7 @@
 #pragma once
 #include "mesh.h"
 #include <stdint.h>
+#include <math.h>
 
 #ifdef __CUDA_ARCH__
 #define MFE_DMUL(a, b) __dmul_rn((a), (b))
@@ -181,6 +182,51 @@ MFE_HD DotMap dot_leaf_map_products(const double *prod, int n, int hyp)
     if (!dot_term_offsets(prod[i], hyp, t0, t1)) return dot_invalid();
     dot_append(m, t0, t1);
   }
+  return m;
+}
+
+// Floating-point formulation of dot_leaf_map_products (same maps, ~4x fewer instructions on the GPU):
+// v = p/U is formed exactly by two power-of-two scalings, t = rint(v) is the round-to-nearest-even offset, and an
+// exact tie (|v - trunc(v)| == 0.5) offers the even candidate r and the odd candidate 2v - r, chosen by the parity
+// of the offset accumulated so far.  Offsets are exact integers in double while |a| <= 2^53; anything larger can
+// never pass dot_apply's range check, so inexactness there is harmless.
+MFE_HD double dot_pow2(int k)   // 2^k for k in [-1022, 1023]
+{
+  return MFE_U2D((uint64_t)(k + 1023) << 52);
+}
+MFE_HD bool dot_is_odd(double a) { return (((long long)a) & 1LL) != 0; }
+
+MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
+{
+  if (n <= 0) return dot_identity();
+  if (hyp < 0) return dot_invalid();
+  if (hyp == HYP_ZERO) {
+    for (int i = 0; i < n; ++i) if (!dot_is_zero(prod[i])) return dot_invalid();
+    return dot_zero_map();
+  }
+  const int k = 1075 - (hyp & 0x7ff);                 // v = p * 2^k, k in [-971, 1074]
+  const int k1 = k / 2, k2 = k - k1;
+  const double c1 = dot_pow2(k1);
+  const double c2 = ((hyp >> 11) & 1) ? -dot_pow2(k2) : dot_pow2(k2);   // offsets relative to the sign of the sum
+  double A0 = 0.0, A1 = 0.0, lo = 1.152921504606846976e18, hi = -1.152921504606846976e18;   // +-2^60
+  for (int i = 0; i < n; ++i) {
+    const double v = MFE_DMUL(MFE_DMUL(prod[i], c1), c2);
+    if (!(fabs(v) < 4503599627370496.0)) return dot_invalid();        // |v| >= 2^52, inf or nan: leaves the binade
+    const double r = rint(v);
+    const double fr = v - trunc(v);
+    if (fabs(fr) == 0.5) {
+      const double o = MFE_DADD(MFE_DADD(v, v), -r);                    // the odd neighbour
+      A0 += dot_is_odd(A0) ? o : r;                                    // entered even: keep S + A0 even
+      A1 += dot_is_odd(A1) ? r : o;                                    // entered odd:  keep S + A1 even (A1 odd)
+    } else { A0 += r; A1 += r; }
+    const double mn = A0 < A1 ? A0 : A1, mx = A0 < A1 ? A1 : A0;
+    lo = mn < lo ? mn : lo;
+    hi = mx > hi ? mx : hi;
+  }
+  // dot_apply needs 2^52 < S + lo and S + hi < 2^53 with 2^52 <= S < 2^53: a usable map has |lo|,|hi| < 2^52
+  if (!(lo > -4503599627370496.0 && hi < 4503599627370496.0)) return dot_invalid();
+  DotMap m;
+  m.a0 = (long long)A0; m.a1 = (long long)A1; m.lo = (long long)lo; m.hi = (long long)hi; m.hyp = hyp; m.pad = 0;
   return m;
 }
 

@@ -262,16 +262,34 @@ struct MatvecCfg {
   static constexpr int SLOT_BYTES = ((CAP * 12 + 127) / 128) * 128;
 };
 
+enum { MV_STREAM_HINT = 1, MV_PREFETCH = 2, MV_X_KEEP = 4 };
+
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ double ldg_keep(const double *p, uint64_t policy)
+{
+  double v;
+  asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 template <int TR, int G, int S>
 __global__ void __launch_bounds__(TR *G, 1)
 k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
          const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
-         int64_t ntiles, int64_t nnz_padded, double *__restrict__ tile_sums, const CgScalars *gate, int k)
+         int64_t ntiles, int64_t nnz_padded, int64_t xlen, int flags, int zmask, double *__restrict__ tile_sums, const CgScalars *gate, int k)
 {
   if (cg_gate_closed(gate, k)) return;
   constexpr int CAP = MatvecCfg<TR>::CAP;
   constexpr int SLOT = MatvecCfg<TR>::SLOT_BYTES;
   constexpr int NW = TR / 32;
+  constexpr int U = 27;                               // one pass covers a whole stencil row
   extern __shared__ __align__(128) unsigned char smem[];
   const int group = threadIdx.x / TR, tg = threadIdx.x % TR;
   unsigned char *gbase = smem + (size_t)group * S * SLOT;
@@ -279,6 +297,11 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   double *wsum = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + G * S * 8) + group * 2 * NW;   // [2][NW], by tile parity
 
   const int64_t gg = (int64_t)blockIdx.x * G + group, stride = (int64_t)gridDim.x * G;
+  uint64_t pol_stream = 0, pol_keep = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+  const bool hint = (flags & MV_STREAM_HINT) != 0, pref = (flags & MV_PREFETCH) != 0, xkeep = (flags & MV_X_KEEP) != 0;
+  const int64_t pf_delta = stride * TR;               // rows between this tile and the group's next tile
 
   auto issue = [&](int64_t t, int s) {
     const int64_t a0 = tile_base[t] & ~3LL;
@@ -289,8 +312,13 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     double *sc = reinterpret_cast<double *>(gbase + (size_t)s * SLOT);
     int *si = reinterpret_cast<int *>(gbase + (size_t)s * SLOT + CAP * 8);
     mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
-    bulk_g2s(sc, coefs + a0, (uint32_t)(n * 8), &bars[s]);
-    bulk_g2s(si, cols + a0, (uint32_t)(n * 4), &bars[s]);
+    if (hint) {
+      bulk_g2s_hint(sc, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
+      bulk_g2s_hint(si, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+    } else {
+      bulk_g2s(sc, coefs + a0, (uint32_t)(n * 8), &bars[s]);
+      bulk_g2s(si, cols + a0, (uint32_t)(n * 4), &bars[s]);
+    }
   };
 
   if (tg == 0) {
@@ -340,17 +368,33 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
         const int len = (int)(o1 - o0);
         // first entry of this row inside the stage: 32-bit difference to the tile's first row + tile skew
         const int base = (int)(uint32_t)(o0 - (uint32_t)tb0) + (int)(tb0 - a0);
-        for (int i0 = 0; i0 < len; i0 += 9) {
-          double cv[9], xv[9];
+        if (pref && len > 0) {
+          // The x entries first touched by the group's NEXT tile are, for a banded matrix, this row's largest
+          // columns shifted by the row distance: pull them into L2 now (a hint only: any in-range address is safe).
+          const int p0 = len - (len + 2) / 3;
+          for (int i = p0; i < len; ++i) {
+            int64_t c = (int64_t)si[base + i] + pf_delta;
+            if (c < xlen) prefetch_l2(x + c);
+          }
+        }
+        for (int i0 = 0; i0 < len; i0 += U) {
+          double cv[U], xv[U];
 #pragma unroll
-          for (int u = 0; u < 9; ++u) {
+          for (int u = 0; u < U; ++u) {
             const bool ok = i0 + u < len;
             const int ii = ok ? base + i0 + u : base;
             cv[u] = sc[ii];
-            xv[u] = __ldg(x + si[ii]);
+            xv[u] = xkeep ? ldg_keep(x + si[ii], pol_keep) : __ldg(x + si[ii]);
           }
+          // All U gathers must be in flight before the dependent add chain starts (the SM issues in order: an add
+          // placed between the loads would serialise them).  Fold a bit of every gathered value into a token that
+          // is masked to zero at run time (zmask == 0) and seed the chain with it: +0.0 for i0 == 0, exact.
+          unsigned tok = 0;
 #pragma unroll
-          for (int u = 0; u < 9; ++u)
+          for (int u = 0; u < U; ++u) tok |= (unsigned)__double2hiint(xv[u]);
+          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+#pragma unroll
+          for (int u = 0; u < U; ++u)
             if (i0 + u < len) sum = __dadd_rn(sum, __dmul_rn(cv[u], xv[u]));
         }
       }
@@ -561,7 +605,6 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
   __shared__ double prod[DOT_CTA_THREADS * (DOT_LEAF + 1)];     // leaf t at [t*(LEAF+1) ...): conflict-free
   __shared__ double wtot[DOT_CTA_THREADS / 32];
   __shared__ int hyps[DOT_CTA_THREADS + 1];
-  __shared__ DotMap wmaps[DOT_CTA_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t base = (int64_t)blockIdx.x * DOT_CHUNK;
   if (blockIdx.x == 0 && tid == 0) { /* dirty_count is reset by the walker of the previous dot */ }
@@ -594,7 +637,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
   if (tid == 0) hyps[DOT_CTA_THREADS] = dot_hyp_of(w.chunk_prefix[blockIdx.x + 1]);
   __syncthreads();
   const int hyp_end = hyps[tid + 1];
-  DotMap m = dot_leaf_map_products(mine, cnt, hyp);
+  DotMap m = dot_leaf_map_products_fp(mine, cnt, hyp);
   const bool dirty = cnt > 0 && (m.hyp == HYP_INVALID || hyp != hyp_end);
   const int any_dirty = __syncthreads_or(dirty ? 1 : 0);
   if (any_dirty) {
@@ -606,13 +649,17 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
     if (tid == 0) w.cta_maps[blockIdx.x] = dot_invalid();
     return;
   }
-  m = warp_compose(m, lane);
-  if (lane == 31) wmaps[warp] = m;
+  // clean chunk: collapse the 256 leaf maps.  They are parked in shared memory (the products are dead now) in a
+  // transposed order so that warp 0 reads them conflict-free: lane l composes leaves 8l..8l+7, then a shuffle scan.
+  DotMap *lm = reinterpret_cast<DotMap *>(prod);
+  lm[(tid & 7) * 32 + (tid >> 3)] = m;
   __syncthreads();
-  if (tid == 0) {
-    DotMap c = wmaps[0];
-    for (int q = 1; q < DOT_CTA_THREADS / 32; ++q) c = dot_compose(c, wmaps[q]);
-    w.cta_maps[blockIdx.x] = c;
+  if (warp == 0) {
+    DotMap c = lm[lane];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) c = dot_compose(c, lm[q * 32 + lane]);
+    c = warp_compose(c, lane);
+    if (lane == 31) w.cta_maps[blockIdx.x] = c;
   }
 }
 
@@ -674,9 +721,14 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
       if (len > 256) continue;
       DotMap m = dot_identity();
       if (len > 0) {
-        const int per = (len + 31) / 32;
+        const int per = (len + 31) / 32;             // <= 8
         const int b = pc.begin + lane * per, e = min(pc.end, b + per);
-        for (int i = b; i < e; ++i) m = dot_compose(m, pc.kind == 0 ? w.leaf_maps[i] : w.cta_maps[i]);
+        const DotMap *src = pc.kind == 0 ? w.leaf_maps : w.cta_maps;
+        DotMap buf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (b + q < e) buf[q] = src[b + q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (b + q < e) m = dot_compose(m, buf[q]);
         m = warp_compose(m, lane);
       }
       if (lane == 31) pmaps[pi] = m;
@@ -689,7 +741,14 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
       const int per = (len + WALK_THREADS - 1) / WALK_THREADS;
       const int b = pc.begin + tid * per, e = min(pc.end, b + per);
       DotMap m = dot_identity();
-      for (int i = b; i < e; ++i) m = dot_compose(m, pc.kind == 0 ? w.leaf_maps[i] : w.cta_maps[i]);
+      const DotMap *src = pc.kind == 0 ? w.leaf_maps : w.cta_maps;
+      for (int i0 = b; i0 < e; i0 += 8) {
+        DotMap buf[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (i0 + q < e) buf[q] = src[i0 + q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (i0 + q < e) m = dot_compose(m, buf[q]);
+      }
       m = warp_compose(m, lane);
       if (lane == 31) wred[warp] = m;
       __syncthreads();

@@ -7,6 +7,8 @@
 #include <cstring>
 #include <vector>
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "../minife_b200/csrc/mesh.h"
 #include "../minife_b200/csrc/hex8.h"
@@ -199,7 +201,7 @@ void hs_tables(double *grad192, double *psi64) { hex8_tables(grad192, psi64); }
 
 // The exact-dot pipeline (k_chunk_sums -> k_chunk_prefix -> k_dot_maps -> k_dot_walk) executed sequentially with
 // the same per-thread arithmetic.  stats[0] = dirty leaves, stats[1] = 1 if the whole-vector replay path ran,
-// stats[2] = pieces whose collapsed map failed its check.
+// stats[2] = pieces whose collapsed map failed its check, stats[3] = leaves where the fp and integer map formulations disagree.
 double hs_exact_dot(long long n, const double *x, const double *y, long long *stats)
 {
   const int nchunks = (int)((n + DOT_CHUNK - 1) / DOT_CHUNK);
@@ -222,6 +224,7 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
   }
   { double pre = 0.0; for (int c = 0; c < nchunks; ++c) { chunk_prefix[c] = pre; pre += chunk_sums[c]; } chunk_prefix[nchunks] = pre; }
 
+  if (stats) stats[3] = 0;
   std::vector<DotMap> cta_maps(nchunks + 1), leaf_maps((size_t)(nchunks + 1) * DOT_CTA_THREADS);
   std::vector<int> dirty_list;
   long long dirty_count = 0;
@@ -254,7 +257,13 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
     hyps[DOT_CTA_THREADS] = dot_hyp_of(chunk_prefix[c + 1]);
     DotMap lm[DOT_CTA_THREADS]; bool any = false; bool dl[DOT_CTA_THREADS];
     for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      lm[t] = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
+      lm[t] = dot_leaf_map_products_fp(prod[t], cnt[t], hyps[t]);
+      {   // the integer formulation must agree wherever it yields a map that could pass dot_apply
+        const DotMap li = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
+        const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && li.lo == lm[t].lo && li.hi == lm[t].hi;
+        const bool int_unusable = li.hyp >= 0 && li.hyp != HYP_ZERO && (li.hi >= (1LL << 52) || li.lo <= -(1LL << 52) || li.hi - li.lo >= (1LL << 52) - 2);
+        if (!same && !(lm[t].hyp == HYP_INVALID && int_unusable) && stats) { stats[3]++; if (getenv("HS_DEBUG")) fprintf(stderr, "leaf %d cnt %d hyp %d: int(%d %lld %lld %lld %lld) fp(%d %lld %lld %lld %lld)\n", t, cnt[t], hyps[t], li.hyp, li.a0, li.a1, li.lo, li.hi, lm[t].hyp, lm[t].a0, lm[t].a1, lm[t].lo, lm[t].hi); }
+      }
       dl[t] = cnt[t] > 0 && (lm[t].hyp == HYP_INVALID || hyps[t] != hyps[t + 1]);
       any = any || dl[t];
     }

@@ -11,6 +11,7 @@ ap.add_argument("--nx", type=int, default=256)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--configs", default="0,1,2,3,4,5,6,7,8,9")
 ap.add_argument("--iters", type=int, default=20)
+ap.add_argument("--flags", default="3")
 args = ap.parse_args()
 n = args.nx
 g = mf.Box([0, n, 0, n, 0, n])
@@ -25,10 +26,13 @@ print(json.dumps({"setup": {p: mesh.phase_ms(p) for p in ("structure", "assembly
 mvb = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N
 for cfg in [int(c) for c in args.configs.split(",") if c != ""]:
     mesh.set_option("matvec_config", cfg)
-    for what in ("matvec", "matvec_dot"):
-        ms = mesh.time_kernel(what, args.reps)
-        print(json.dumps({"kernel": what, "config": cfg, "ms": ms, "GBs": mvb / ms / 1e6}))
-mesh.set_option("matvec_config", 0)
+    for fl in [int(f) for f in args.flags.split(",")]:
+        mesh.set_option("matvec_flags", fl)
+        for what in ("matvec", "matvec_dot"):
+            ms = mesh.time_kernel(what, args.reps)
+            print(json.dumps({"kernel": what, "config": cfg, "flags": fl, "ms": ms, "GBs": mvb / ms / 1e6}))
+mesh.set_option("matvec_config", 4)
+mesh.set_option("matvec_flags", 3)
 for what, byts in (("matvec_simple", mvb), ("waxpby", 24.0 * N), ("xr_update", 48.0 * N), ("dot_rr", 8.0 * N), ("dot_pap", 16.0 * N)):
     for mode in ((0, 1, 2) if what.startswith("dot") else (0,)):
         if mode == 1 and n > 64:
