@@ -123,9 +123,9 @@ struct mfe_ctx {
   double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
   int dot_mode = MFE_DOT_EXACT;
   int op_timing = 1;
-  int mv_cfg = 4;                // SpMV configuration (see matvec_configs): 64 rows x 5 groups x 2 stages
-  int tr = 64;                   // rows per SpMV tile of that configuration
-  int mv_flags = MV_STREAM_HINT | MV_PREFETCH;
+  int mv_cfg = 9;                // SpMV configuration (see matvec_configs): 32 rows x 10 groups x 2 stages
+  int tr = 32;                   // rows per SpMV tile of that configuration
+  int mv_flags = MV_STREAM_HINT;
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -244,7 +244,6 @@ extern "C" mfe_ctx *mfe_create(int rank, int nranks, int device, const int globa
   cudaMemcpyToSymbol(c_grad, grad, sizeof grad);
   cudaMemcpyToSymbol(c_psi, psi, sizeof psi);
   if (dev_alloc(&c->d_sc, 1) || dev_alloc(&c->d_gather, nranks)) { delete c; return nullptr; }
-  cudaFuncSetAttribute(k_dot_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DOT_MAX_DIRTY * DOT_LEAF * sizeof(double)));
   cudaMemset(c->d_sc, 0, sizeof(CgScalars));
   if ((e = cudaGetLastError()) != cudaSuccess) { fail("mfe_create: %s", cudaGetErrorString(e)); delete c; return nullptr; }
   return c;
@@ -259,7 +258,8 @@ static void free_vectors(mfe_ctx *c)
 {
   free_dev(c->d_b); free_dev(c->d_x); free_dev(c->d_r); free_dev(c->d_p); free_dev(c->d_Ap); free_dev(c->d_tmp1); free_dev(c->d_tmp2);
   free_dev(c->d_tile_sums); free_dev(c->dot.w.chunk_sums); free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps);
-  free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.chunk_tmp);
+  free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.warp_maps); free_dev(c->dot.w.super_maps); free_dev(c->dot.w.hyper_maps);
+  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.chunk_tmp);
   c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = c->d_tile_sums = nullptr;
   c->dot = DotWs();
   c->vec_cap = 0;
@@ -325,9 +325,13 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
   const int64_t ntiles = (need + 31) / 32;
   if (dev_alloc(&c->d_tile_sums, ntiles + 1) || dev_alloc(&c->dot.w.chunk_sums, nchunks + 1) || dev_alloc(&c->dot.w.chunk_prefix, nchunks + 2) ||
       dev_alloc(&c->dot.w.cta_maps, nchunks + 1) || dev_alloc(&c->dot.w.leaf_maps, (nchunks + 1) * DOT_CTA_THREADS) ||
+      dev_alloc(&c->dot.w.warp_maps, (nchunks + 1) * (DOT_CTA_THREADS / 32)) || dev_alloc(&c->dot.w.super_maps, nchunks / 32 + 2) ||
+      dev_alloc(&c->dot.w.hyper_maps, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.super_cnt, nchunks / 32 + 2) || dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) ||
       dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) || dev_alloc(&c->dot.w.result, 1) ||
       dev_alloc(&c->dot.chunk_tmp, nchunks + 1)) return 1;
   CK(cudaMemsetAsync(c->dot.w.dirty_count, 0, sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->dot.w.super_cnt, 0, sizeof(int) * (nchunks / 32 + 2), c->stream));
+  CK(cudaMemsetAsync(c->dot.w.hyper_cnt, 0, sizeof(int) * (nchunks / 1024 + 2), c->stream));
   c->vec_cap = need;
   return 0;
 }
@@ -605,7 +609,7 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
       c->launches++;
     } else {
       if (nchunks > 0) { k_dot_maps<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k); c->launches++; }
-      k_dot_walk<<<1, WALK_THREADS, DOT_MAX_DIRTY * DOT_LEAF * sizeof(double), c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
+      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
       c->launches++;
     }
   }

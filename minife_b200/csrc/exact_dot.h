@@ -196,6 +196,28 @@ MFE_HD double dot_pow2(int k)   // 2^k for k in [-1022, 1023]
 }
 MFE_HD bool dot_is_odd(double a) { return (((long long)a) & 1LL) != 0; }
 
+MFE_HD double dot_fmin(double a, double b) { return a < b ? a : b; }
+MFE_HD double dot_fmax(double a, double b) { return a > b ? a : b; }
+
+// One term of the fp formulation.  vmax collects max|v| (range check deferred to the end of the leaf), nt counts
+// exact ties: after nt ties the odd-entry trajectory differs from the even-entry one by at most nt, so lo/hi are
+// tracked on the even-entry offset A0 only and widened by nt at the end (conservative).
+#define MFE_DOT_FP_TERM(p)                                                                                  \
+  {                                                                                                         \
+    const double v = MFE_DMUL(MFE_DMUL((p), c1), c2);                                                       \
+    const double av = fabs(v);                                                                              \
+    vmax = av > vmax ? av : vmax;                                                                           \
+    const double r = rint(v);                                                                               \
+    if (fabs(v - r) == 0.5) {                              /* exact tie: even candidate r, odd 2v - r */  \
+      const double o = MFE_DADD(MFE_DADD(v, v), -r);                                                        \
+      A0 += dot_is_odd(A0) ? o : r;                                                                         \
+      A1 += dot_is_odd(A1) ? r : o;                                                                         \
+      nt += 1.0;                                                                                            \
+    } else { A0 += r; A1 += r; }                                                                            \
+    lo = A0 < lo ? A0 : lo;                                                                                 \
+    hi = A0 > hi ? A0 : hi;                                                                                 \
+  }
+
 MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
 {
   if (n <= 0) return dot_identity();
@@ -208,23 +230,20 @@ MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
   const int k1 = k / 2, k2 = k - k1;
   const double c1 = dot_pow2(k1);
   const double c2 = ((hyp >> 11) & 1) ? -dot_pow2(k2) : dot_pow2(k2);   // offsets relative to the sign of the sum
-  double A0 = 0.0, A1 = 0.0, lo = 1.152921504606846976e18, hi = -1.152921504606846976e18;   // +-2^60
-  for (int i = 0; i < n; ++i) {
-    const double v = MFE_DMUL(MFE_DMUL(prod[i], c1), c2);
-    if (!(fabs(v) < 4503599627370496.0)) return dot_invalid();        // |v| >= 2^52, inf or nan: leaves the binade
-    const double r = rint(v);
-    const double fr = v - trunc(v);
-    if (fabs(fr) == 0.5) {
-      const double o = MFE_DADD(MFE_DADD(v, v), -r);                    // the odd neighbour
-      A0 += dot_is_odd(A0) ? o : r;                                    // entered even: keep S + A0 even
-      A1 += dot_is_odd(A1) ? r : o;                                    // entered odd:  keep S + A1 even (A1 odd)
-    } else { A0 += r; A1 += r; }
-    const double mn = A0 < A1 ? A0 : A1, mx = A0 < A1 ? A1 : A0;
-    lo = mn < lo ? mn : lo;
-    hi = mx > hi ? mx : hi;
+  double A0 = 0.0, A1 = 0.0, lo = 1.152921504606846976e18, hi = -1.152921504606846976e18, vmax = 0.0, nt = 0.0;
+  if (n == DOT_LEAF) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < DOT_LEAF; ++i) MFE_DOT_FP_TERM(prod[i])
+  } else {
+    for (int i = 0; i < n; ++i) MFE_DOT_FP_TERM(prod[i])
   }
-  // dot_apply needs 2^52 < S + lo and S + hi < 2^53 with 2^52 <= S < 2^53: a usable map has |lo|,|hi| < 2^52
-  if (!(lo > -4503599627370496.0 && hi < 4503599627370496.0)) return dot_invalid();
+  lo -= nt; hi += nt;
+  // |v| >= 2^52 (or inf): the term alone leaves the binade.  nan: A0 is nan.  dot_apply needs 2^52 < S + lo and
+  // S + hi < 2^53 with 2^52 <= S < 2^53, so a usable map has |lo|,|hi| < 2^52.
+  if (!(vmax < 4503599627370496.0) || !(A0 == A0) || !(A1 == A1) || !(lo > -4503599627370496.0 && hi < 4503599627370496.0))
+    return dot_invalid();
   DotMap m;
   m.a0 = (long long)A0; m.a1 = (long long)A1; m.lo = (long long)lo; m.hi = (long long)hi; m.hyp = hyp; m.pad = 0;
   return m;
@@ -249,84 +268,117 @@ MFE_HD bool dot_apply(const DotMap &m, double &s)
 // the literal loop of the reference over [begin,end)
 MFE_HD double dot_replay(const double *x, const double *y, long long begin, long long end, double s)
 {
-  for (long long i = begin; i < end; ++i) s = MFE_DADD(s, MFE_DMUL(x[i], y[i]));
+  long long i = begin;
+#ifdef __CUDA_ARCH__
+  for (; i + 16 <= end; i += 16) {        // 32 independent loads in flight, then the ordered adds
+    double p[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) p[q] = MFE_DMUL(x[i + q], y[i + q]);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s = MFE_DADD(s, p[q]);
+  }
+#endif
+  for (; i < end; ++i) s = MFE_DADD(s, MFE_DMUL(x[i], y[i]));
   return s;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// workspace + the sequential part of the walk (shared by k_dot_walk and the CPU test harness)
+// Map hierarchy + the sequential part of the walk (shared by the kernels and the CPU test harness).
+//   level 0  leaf   DOT_LEAF terms            leaf_maps   (stored for dirty chunks only)
+//   level 1  warp   32 leaves                 warp_maps   (stored for dirty chunks only)
+//   level 2  chunk  8 warps  = 256 leaves     cta_maps
+//   level 3  super  32 chunks = 8192 leaves   super_maps
+//   level 4  hyper  32 supers = 262144 leaves hyper_maps
+// A clean stretch of leaves [lo,hi) between two dirty leaves decomposes, segment-tree style, into <= 9 runs of
+// consecutive same-level maps (ascending levels, the hypers, descending levels), each run <= 31 long below the
+// top level: one warp collapses a run with a single coalesced load and an ordered shuffle scan.
 // ---------------------------------------------------------------------------------------------------------
+enum { DOT_LEVELS = 5, DOT_GAP_PIECES = 9 };
+MFE_HD int dot_level_size(int level)   // in leaves
+{
+  return level == 0 ? 1 : level == 1 ? 32 : level == 2 ? 256 : level == 3 ? 8192 : 262144;
+}
+
 struct DotWork {
   double *chunk_sums;      // nchunks plain partial sums (binade prediction)
   double *chunk_prefix;    // nchunks + 1 exclusive prefix of the above
-  DotMap *cta_maps;        // nchunks
-  DotMap *leaf_maps;       // nchunks * DOT_CTA_THREADS (written for dirty chunks only)
+  DotMap *leaf_maps;       // level 0: nchunks * 256
+  DotMap *warp_maps;       // level 1: nchunks * 8
+  DotMap *cta_maps;        // level 2: nchunks       (pad = 1 marks a dirty chunk: its level 0/1 maps are stored)
+  DotMap *super_maps;      // level 3: ceil(nchunks / 32)
+  DotMap *hyper_maps;      // level 4: ceil(nsupers / 32)
+  int *super_cnt;          // arrival tickets (self-resetting)
+  int *hyper_cnt;
   int *dirty_count;        // 1
   int *dirty_list;         // DOT_MAX_DIRTY leaf indices
   double *result;          // 1
 };
-
-enum { WALK_MAX_PIECES = 3 * (DOT_MAX_DIRTY + 1) };
-struct WalkPiece { int kind; int begin; int end; };      // kind 0: leaf maps [begin,end), 1: chunk maps [begin,end)
-
-// The clean stretch between dirty leaf g-1 and dirty leaf g (sorted ascending; g = 0..D) splits into
-// [head leaves of a dirty chunk][full clean chunks][tail leaves of the next dirty chunk].
-MFE_HD void dot_gap_pieces(int g, int D, const int *sorted, int nleaves, WalkPiece *out3)
+MFE_HD const DotMap *dot_level_maps(const DotWork &w, int level)
 {
-  const int lo = g == 0 ? 0 : sorted[g - 1] + 1, hi = g == D ? nleaves : sorted[g];
-  WalkPiece p0 = { 0, 0, 0 }, p1 = { 1, 0, 0 }, p2 = { 0, 0, 0 };
-  if (lo < hi) {
-    const int cfirst = (lo + DOT_CTA_THREADS - 1) / DOT_CTA_THREADS;    // first full chunk
-    const int clast = hi / DOT_CTA_THREADS;                              // one past the last full chunk
-    if (cfirst > clast) { p0.begin = lo; p0.end = hi; }                  // inside one chunk
-    else {
-      p0.begin = lo; p0.end = cfirst * DOT_CTA_THREADS;                  // head leaves (may be empty)
-      p1.begin = cfirst; p1.end = clast;
-      p2.begin = clast * DOT_CTA_THREADS; p2.end = hi;                   // tail leaves (may be empty)
-    }
-  }
-  out3[0] = p0; out3[1] = p1; out3[2] = p2;
+  return level == 0 ? w.leaf_maps : level == 1 ? w.warp_maps : level == 2 ? w.cta_maps : level == 3 ? w.super_maps : w.hyper_maps;
 }
 
-// a piece whose collapsed map failed its check: apply its members one by one, replaying the failing ones
-MFE_HD double dot_walk_piece_slow(const WalkPiece &pc, const DotWork &w, const double *x, const double *y, long long n, double s)
+struct WalkPiece { int level; int begin; int count; };   // `count` consecutive level-`level` maps starting at `begin`
+
+// clean leaves [lo,hi) -> out[DOT_GAP_PIECES] (unused entries have count 0), in application order
+MFE_HD void dot_gap_decompose(long long lo, long long hi, WalkPiece *out)
 {
-  if (pc.kind == 0) {
-    for (int l = pc.begin; l < pc.end; ++l) {
-      const DotMap m = w.leaf_maps[l];
-      if (!dot_apply(m, s)) {
-        const long long b = (long long)l * DOT_LEAF, e = b + DOT_LEAF < n ? b + DOT_LEAF : n;
-        s = dot_replay(x, y, b, e, s);
-      }
+  for (int i = 0; i < DOT_GAP_PIECES; ++i) { out[i].level = 0; out[i].begin = 0; out[i].count = 0; }
+  long long a = lo;
+  int np = 0;
+  for (int k = 0; k < DOT_LEVELS - 1; ++k) {          // ascend: align `a` to the next level
+    const long long sz = dot_level_size(k), up = dot_level_size(k + 1);
+    int cnt = 0; const long long first = a / sz;
+    while (a % up != 0 && a + sz <= hi) { a += sz; ++cnt; }
+    out[np].level = k; out[np].begin = (int)first; out[np].count = cnt; ++np;
+  }
+  {
+    const long long sz = dot_level_size(DOT_LEVELS - 1);
+    int cnt = 0; const long long first = a / sz;
+    while (a + sz <= hi) { a += sz; ++cnt; }
+    out[np].level = DOT_LEVELS - 1; out[np].begin = (int)first; out[np].count = cnt; ++np;
+  }
+  for (int k = DOT_LEVELS - 2; k >= 0; --k) {          // descend towards hi
+    const long long sz = dot_level_size(k);
+    int cnt = 0; const long long first = a / sz;
+    while (a + sz <= hi) { a += sz; ++cnt; }
+    out[np].level = k; out[np].begin = (int)first; out[np].count = cnt; ++np;
+  }
+}
+
+// Slow but always-correct application of one map of the hierarchy: descend into the children when the map fails
+// its check; replay the terms when there is nothing stored below.
+MFE_HD double dot_apply_or_descend(const DotWork &w, int level, long long index, const double *x, const double *y, long long n, double s)
+{
+  // explicit stack instead of recursion (device friendly): (level, index) pairs, children pushed in reverse order
+  int lv[DOT_LEVELS * 32]; long long ix[DOT_LEVELS * 32]; int sp = 0;
+  lv[sp] = level; ix[sp] = index; ++sp;
+  while (sp > 0) {
+    --sp;
+    const int L = lv[sp]; const long long I = ix[sp];
+    const long long b = I * dot_level_size(L) * DOT_LEAF;
+    if (b >= n) continue;
+    const DotMap m = dot_level_maps(w, L)[I];
+    if (dot_apply(m, s)) continue;
+    bool children_stored = L >= 3 || (L == 2 && m.pad == 1) || L == 1;
+    if (L == 0 || !children_stored) {
+      long long e = b + (long long)dot_level_size(L) * DOT_LEAF; if (e > n) e = n;
+      s = dot_replay(x, y, b, e, s);
+      continue;
     }
-  } else {
-    for (int c = pc.begin; c < pc.end; ++c) {
-      const DotMap m = w.cta_maps[c];
-      if (!dot_apply(m, s)) {
-        const long long b = (long long)c * DOT_CHUNK, e = b + DOT_CHUNK < n ? b + DOT_CHUNK : n;
-        s = dot_replay(x, y, b, e, s);
-      }
-    }
+    const int fan = L == 2 ? 8 : 32;
+    for (int q = fan - 1; q >= 0; --q) { lv[sp] = L - 1; ix[sp] = I * fan + q; ++sp; }
   }
   return s;
 }
 
-// the sequential walk: [pieces of gap 0][dirty leaf 0][pieces of gap 1][dirty leaf 1] ... [pieces of gap D]
-MFE_HD double dot_walk_final(int D, const int *sorted, const WalkPiece *pieces, const DotMap *pmaps, const DotWork &w,
-                             const double *x, const double *y, long long n)
+// a gap whose collapsed map failed: piece by piece, map by map
+MFE_HD double dot_walk_gap_slow(long long lo, long long hi, const DotWork &w, const double *x, const double *y, long long n, double s)
 {
-  double s = 0.0;
-  for (int g = 0; g <= D; ++g) {
-    for (int q = 0; q < 3; ++q) {
-      const WalkPiece pc = pieces[3 * g + q];
-      if (pc.end <= pc.begin) continue;
-      if (!dot_apply(pmaps[3 * g + q], s)) s = dot_walk_piece_slow(pc, w, x, y, n, s);
-    }
-    if (g < D) {
-      const long long b = (long long)sorted[g] * DOT_LEAF, e = b + DOT_LEAF < n ? b + DOT_LEAF : n;
-      s = dot_replay(x, y, b, e, s);
-    }
-  }
+  WalkPiece pc[DOT_GAP_PIECES];
+  dot_gap_decompose(lo, hi, pc);
+  for (int q = 0; q < DOT_GAP_PIECES; ++q)
+    for (int i = 0; i < pc[q].count; ++i) s = dot_apply_or_descend(w, pc[q].level, (long long)pc[q].begin + i, x, y, n, s);
   return s;
 }
 

@@ -640,27 +640,69 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
   DotMap m = dot_leaf_map_products_fp(mine, cnt, hyp);
   const bool dirty = cnt > 0 && (m.hyp == HYP_INVALID || hyp != hyp_end);
   const int any_dirty = __syncthreads_or(dirty ? 1 : 0);
+  DotMap cmap;                                      // chunk map (valid on warp 0, lane 31)
   if (any_dirty) {
+    // dirty chunk: keep the leaf maps and the 8 warp maps so that the walker can stitch around the dirty leaves
     w.leaf_maps[(int64_t)blockIdx.x * DOT_CTA_THREADS + tid] = m;
     if (dirty) {
       const int slot = atomicAdd(w.dirty_count, 1);
       if (slot < DOT_MAX_DIRTY) w.dirty_list[slot] = blockIdx.x * DOT_CTA_THREADS + tid;
     }
-    if (tid == 0) w.cta_maps[blockIdx.x] = dot_invalid();
-    return;
-  }
-  // clean chunk: collapse the 256 leaf maps.  They are parked in shared memory (the products are dead now) in a
-  // transposed order so that warp 0 reads them conflict-free: lane l composes leaves 8l..8l+7, then a shuffle scan.
-  DotMap *lm = reinterpret_cast<DotMap *>(prod);
-  lm[(tid & 7) * 32 + (tid >> 3)] = m;
-  __syncthreads();
-  if (warp == 0) {
-    DotMap c = lm[lane];
+    const DotMap wm = warp_compose(m, lane);
+    if (lane == 31) w.warp_maps[(int64_t)blockIdx.x * (DOT_CTA_THREADS / 32) + warp] = wm;
+    cmap = dot_invalid();
+    cmap.pad = 1;
+  } else {
+    // clean chunk: collapse the 256 leaf maps.  They are parked in shared memory (the products are dead now) in
+    // a transposed order so that warp 0 reads them conflict-free: lane l composes leaves 8l..8l+7, then a scan.
+    DotMap *lm = reinterpret_cast<DotMap *>(prod);
+    lm[(tid & 7) * 32 + (tid >> 3)] = m;
+    __syncthreads();
+    if (warp == 0) {
+      cmap = lm[lane];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) c = dot_compose(c, lm[q * 32 + lane]);
-    c = warp_compose(c, lane);
-    if (lane == 31) w.cta_maps[blockIdx.x] = c;
+      for (int q = 1; q < 8; ++q) cmap = dot_compose(cmap, lm[q * 32 + lane]);
+      cmap = warp_compose(cmap, lane);
+    }
   }
+  if (warp != 0) return;
+  // level 2 -> 3 -> 4: the last chunk of a group of 32 to arrive collapses the group (arrival tickets reset
+  // themselves, so the workspace is reusable without a memset)
+  const int c = blockIdx.x, nchunks = gridDim.x;
+  const int sgrp = c >> 5, ssize = min(32, nchunks - (sgrp << 5));
+  int last = 0;
+  if (lane == 31) {
+    w.cta_maps[c] = cmap;
+    __threadfence();
+    last = atomicAdd(&w.super_cnt[sgrp], 1) == ssize - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 31);
+  if (!last) return;
+  __threadfence();
+  DotMap sm = dot_identity();
+  if (lane < ssize) {
+    const DotMap *src = w.cta_maps + ((int64_t)sgrp << 5) + lane;
+    sm.a0 = __ldcg(&src->a0); sm.a1 = __ldcg(&src->a1); sm.lo = __ldcg(&src->lo); sm.hi = __ldcg(&src->hi); sm.hyp = __ldcg(&src->hyp); sm.pad = 0;
+  }
+  sm = warp_compose(sm, lane);
+  const int nsupers = (nchunks + 31) >> 5;
+  const int hgrp = sgrp >> 5, hsize = min(32, nsupers - (hgrp << 5));
+  if (lane == 31) {
+    w.super_maps[sgrp] = sm;
+    w.super_cnt[sgrp] = 0;
+    __threadfence();
+    last = atomicAdd(&w.hyper_cnt[hgrp], 1) == hsize - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 31);
+  if (!last) return;
+  __threadfence();
+  DotMap hm = dot_identity();
+  if (lane < hsize) {
+    const DotMap *src = w.super_maps + ((int64_t)hgrp << 5) + lane;
+    hm.a0 = __ldcg(&src->a0); hm.a1 = __ldcg(&src->a1); hm.lo = __ldcg(&src->lo); hm.hi = __ldcg(&src->hi); hm.hyp = __ldcg(&src->hyp); hm.pad = 0;
+  }
+  hm = warp_compose(hm, lane);
+  if (lane == 31) { w.hyper_maps[hgrp] = hm; w.hyper_cnt[hgrp] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -669,8 +711,18 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
 // Any map that fails its check is replayed from global memory in plain floating point, so the result is the
 // serial loop's for every input.
 // ------------------------------------------------------------------------------------------------------
-enum { WALK_THREADS = 1024 };
+enum { WALK_THREADS = 512 };
 
+__device__ __forceinline__ DotMap load_map_cg(const DotMap *src)
+{
+  DotMap m;
+  m.a0 = __ldcg(&src->a0); m.a1 = __ldcg(&src->a1); m.lo = __ldcg(&src->lo); m.hi = __ldcg(&src->hi); m.hyp = __ldcg(&src->hyp); m.pad = __ldcg(&src->pad);
+  return m;
+}
+
+// One CTA.  (1) sort the dirty leaves, fetch their products; (2) one warp per gap: the <= 9 runs of the gap are
+// loaded at once (one map per lane and run) and collapsed by ordered shuffle scans into ONE map per gap;
+// (3) thread 0 walks  [gap 0][dirty leaf 0][gap 1][dirty leaf 1] ... [gap D]  -- ~2 short steps per dirty leaf.
 __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
                                                           DotWork w, int nchunks, CgScalars *sc, int epi, int k,
                                                           double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
@@ -679,21 +731,16 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
   if (cg_gate_closed(gate, k)) return;
   __shared__ int dirty[DOT_MAX_DIRTY];
   __shared__ int sorted[DOT_MAX_DIRTY];
-  __shared__ WalkPiece pieces[WALK_MAX_PIECES];
-  __shared__ DotMap pmaps[WALK_MAX_PIECES];
-  __shared__ DotMap wred[WALK_THREADS / 32];
-  __shared__ int big[WALK_MAX_PIECES];
-  __shared__ int nbig_sh;
-  extern __shared__ double replay_prod[];          // [DOT_MAX_DIRTY][DOT_LEAF] products of the dirty leaves
+  __shared__ DotMap gmaps[DOT_MAX_DIRTY + 1];
+  __shared__ double replay_prod[DOT_MAX_DIRTY * DOT_LEAF];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = *w.dirty_count;
-  const int nleaves = nchunks * DOT_CTA_THREADS;
+  const long long nleaves = (long long)nchunks * DOT_CTA_THREADS;
   double s = 0.0;
   if (D > DOT_MAX_DIRTY) {                     // pathological input: the literal loop
     if (tid == 0) s = dot_replay(x, y, 0, n, 0.0);
   } else {
     for (int i = tid; i < D; i += WALK_THREADS) dirty[i] = w.dirty_list[i];
-    if (tid == 0) nbig_sh = 0;
     __syncthreads();
     for (int i = tid; i < D; i += WALK_THREADS) {        // rank sort (leaf indices are distinct)
       const int v = dirty[i]; int rk = 0;
@@ -706,68 +753,34 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
       const int64_t i = (int64_t)sorted[q / DOT_LEAF] * DOT_LEAF + (q % DOT_LEAF);
       replay_prod[q] = i < n ? __dmul_rn(x[i], y[i]) : 0.0;
     }
-    // pieces of gap g (between dirty leaf g-1 and dirty leaf g) live at pieces[3g .. 3g+2]
-    for (int g = tid; g <= D; g += WALK_THREADS) {
-      dot_gap_pieces(g, D, sorted, nleaves, pieces + 3 * g);
-      for (int q = 0; q < 3; ++q)
-        if (pieces[3 * g + q].end - pieces[3 * g + q].begin > 256) big[atomicAdd(&nbig_sh, 1)] = 3 * g + q;
-    }
-    __syncthreads();
-    const int npieces = 3 * (D + 1), nbig = nbig_sh;
-    // small pieces: one warp each, all warps in parallel
-    for (int pi = warp; pi < npieces; pi += WALK_THREADS / 32) {
-      const WalkPiece pc = pieces[pi];
-      const int len = pc.end - pc.begin;
-      if (len > 256) continue;
-      DotMap m = dot_identity();
-      if (len > 0) {
-        const int per = (len + 31) / 32;             // <= 8
-        const int b = pc.begin + lane * per, e = min(pc.end, b + per);
-        const DotMap *src = pc.kind == 0 ? w.leaf_maps : w.cta_maps;
-        DotMap buf[8];
+    for (int g = warp; g <= D; g += WALK_THREADS / 32) {
+      const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
+      WalkPiece pc[DOT_GAP_PIECES];
+      dot_gap_decompose(lo, hi, pc);
+      DotMap pm[DOT_GAP_PIECES];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) if (b + q < e) buf[q] = src[b + q];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (b + q < e) m = dot_compose(m, buf[q]);
-        m = warp_compose(m, lane);
+      for (int q = 0; q < DOT_GAP_PIECES; ++q) {           // all loads first: one latency for the whole gap
+        pm[q] = dot_identity();
+        if (pc[q].count <= 32) { if (lane < pc[q].count) pm[q] = load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + lane); }
+        else {                                             // only the top level of very long vectors
+          const int per = (pc[q].count + 31) / 32, b = lane * per, e = min(pc[q].count, b + per);
+          for (int i = b; i < e; ++i) pm[q] = dot_compose(pm[q], load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + i));
+        }
       }
-      if (lane == 31) pmaps[pi] = m;
-    }
-    // big pieces: the whole CTA cooperates on each (contiguous sub-range per thread, warp scan, then warp 0)
-    for (int bi = 0; bi < nbig; ++bi) {
-      const int pi = big[bi];
-      const WalkPiece pc = pieces[pi];
-      const int len = pc.end - pc.begin;
-      const int per = (len + WALK_THREADS - 1) / WALK_THREADS;
-      const int b = pc.begin + tid * per, e = min(pc.end, b + per);
-      DotMap m = dot_identity();
-      const DotMap *src = pc.kind == 0 ? w.leaf_maps : w.cta_maps;
-      for (int i0 = b; i0 < e; i0 += 8) {
-        DotMap buf[8];
+      DotMap gm = dot_identity();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) if (i0 + q < e) buf[q] = src[i0 + q];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) if (i0 + q < e) m = dot_compose(m, buf[q]);
+      for (int q = 0; q < DOT_GAP_PIECES; ++q) {
+        if (pc[q].count == 0) continue;                    // warp-uniform
+        const DotMap r = warp_compose(pm[q], lane);
+        gm = dot_compose(gm, r);                           // meaningful on lane 31
       }
-      m = warp_compose(m, lane);
-      if (lane == 31) wred[warp] = m;
-      __syncthreads();
-      if (warp == 0) {
-        DotMap r = wred[lane];
-        r = warp_compose(r, lane);
-        if (lane == 31) pmaps[pi] = r;
-      }
-      __syncthreads();
+      if (lane == 31) gmaps[g] = gm;
     }
     __syncthreads();
     if (tid == 0) {
-      // the sequential walk (dot_walk_final with the dirty leaves replayed from shared memory)
       for (int g = 0; g <= D; ++g) {
-        for (int q = 0; q < 3; ++q) {
-          const WalkPiece pc = pieces[3 * g + q];
-          if (pc.end <= pc.begin) continue;
-          if (!dot_apply(pmaps[3 * g + q], s)) s = dot_walk_piece_slow(pc, w, x, y, n, s);
-        }
+        const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
+        if (lo < hi && !dot_apply(gmaps[g], s)) s = dot_walk_gap_slow(lo, hi, w, x, y, n, s);
         if (g < D) {
           const int64_t b = (int64_t)sorted[g] * DOT_LEAF;
           const int cnt = (int)(b + DOT_LEAF <= n ? DOT_LEAF : n - b);

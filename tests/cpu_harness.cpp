@@ -225,7 +225,9 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
   { double pre = 0.0; for (int c = 0; c < nchunks; ++c) { chunk_prefix[c] = pre; pre += chunk_sums[c]; } chunk_prefix[nchunks] = pre; }
 
   if (stats) stats[3] = 0;
-  std::vector<DotMap> cta_maps(nchunks + 1), leaf_maps((size_t)(nchunks + 1) * DOT_CTA_THREADS);
+  const int nsupers = (nchunks + 31) / 32, nhypers = (nsupers + 31) / 32;
+  std::vector<DotMap> cta_maps(nchunks + 1), leaf_maps((size_t)(nchunks + 1) * DOT_CTA_THREADS), warp_maps((size_t)(nchunks + 1) * 8),
+      super_maps(nsupers + 1), hyper_maps(nhypers + 1);
   std::vector<int> dirty_list;
   long long dirty_count = 0;
   for (int c = 0; c < nchunks; ++c) {      // k_dot_maps
@@ -258,45 +260,57 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
     DotMap lm[DOT_CTA_THREADS]; bool any = false; bool dl[DOT_CTA_THREADS];
     for (int t = 0; t < DOT_CTA_THREADS; ++t) {
       lm[t] = dot_leaf_map_products_fp(prod[t], cnt[t], hyps[t]);
-      {   // the integer formulation must agree wherever it yields a map that could pass dot_apply
+      {   // the integer formulation must agree (offsets exactly; the fp bounds may only be wider) wherever usable
         const DotMap li = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
-        const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && li.lo == lm[t].lo && li.hi == lm[t].hi;
-        const bool int_unusable = li.hyp >= 0 && li.hyp != HYP_ZERO && (li.hi >= (1LL << 52) || li.lo <= -(1LL << 52) || li.hi - li.lo >= (1LL << 52) - 2);
+        const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && lm[t].lo <= li.lo && lm[t].hi >= li.hi && lm[t].lo >= li.lo - 16 && lm[t].hi <= li.hi + 16;
+        const bool int_unusable = li.hyp >= 0 && li.hyp != HYP_ZERO && (li.hi >= (1LL << 52) - 16 || li.lo <= -(1LL << 52) + 16 || li.hi - li.lo >= (1LL << 52) - 2);
         if (!same && !(lm[t].hyp == HYP_INVALID && int_unusable) && stats) { stats[3]++; if (getenv("HS_DEBUG")) fprintf(stderr, "leaf %d cnt %d hyp %d: int(%d %lld %lld %lld %lld) fp(%d %lld %lld %lld %lld)\n", t, cnt[t], hyps[t], li.hyp, li.a0, li.a1, li.lo, li.hi, lm[t].hyp, lm[t].a0, lm[t].a1, lm[t].lo, lm[t].hi); }
       }
       dl[t] = cnt[t] > 0 && (lm[t].hyp == HYP_INVALID || hyps[t] != hyps[t + 1]);
       any = any || dl[t];
     }
+    DotMap cm = dot_identity();
+    for (int t = 0; t < DOT_CTA_THREADS; ++t) cm = dot_compose(cm, lm[t]);
     if (any) {
       for (int t = 0; t < DOT_CTA_THREADS; ++t) {
         leaf_maps[(size_t)c * DOT_CTA_THREADS + t] = lm[t];
         if (dl[t]) { if (dirty_count < DOT_MAX_DIRTY) dirty_list.push_back(c * DOT_CTA_THREADS + t); ++dirty_count; }
       }
-      cta_maps[c] = dot_invalid();
+      for (int wq = 0; wq < 8; ++wq) { DotMap wm = dot_identity(); for (int l = 0; l < 32; ++l) wm = dot_compose(wm, lm[wq * 32 + l]); warp_maps[(size_t)c * 8 + wq] = wm; }
+      cm = dot_invalid(); cm.pad = 1;
     } else {
-      DotMap cm = dot_identity();
-      for (int t = 0; t < DOT_CTA_THREADS; ++t) cm = dot_compose(cm, lm[t]);
-      cta_maps[c] = cm;
+      for (int t = 0; t < DOT_CTA_THREADS; ++t) leaf_maps[(size_t)c * DOT_CTA_THREADS + t] = dot_invalid();   // not stored on the device
+      for (int wq = 0; wq < 8; ++wq) warp_maps[(size_t)c * 8 + wq] = dot_invalid();
     }
+    cta_maps[c] = cm;
   }
+  for (int sg = 0; sg < nsupers; ++sg) { DotMap m = dot_identity(); for (int i = sg * 32; i < std::min(nchunks, sg * 32 + 32); ++i) m = dot_compose(m, cta_maps[i]); m.pad = 0; super_maps[sg] = m; }
+  for (int hg = 0; hg < nhypers; ++hg) { DotMap m = dot_identity(); for (int i = hg * 32; i < std::min(nsupers, hg * 32 + 32); ++i) m = dot_compose(m, super_maps[i]); hyper_maps[hg] = m; }
   if (stats) { stats[0] = dirty_count; stats[1] = 0; stats[2] = 0; }
   if (dirty_count > DOT_MAX_DIRTY) { if (stats) stats[1] = 1; return dot_replay(x, y, 0, n, 0.0); }
   // k_dot_walk
-  const int D = (int)dirty_count, nleaves = nchunks * DOT_CTA_THREADS;
+  const int D = (int)dirty_count; const long long nleaves = (long long)nchunks * DOT_CTA_THREADS;
   std::vector<int> sorted(dirty_list);
   std::sort(sorted.begin(), sorted.end());
-  std::vector<WalkPiece> pieces(3 * (D + 1));
-  std::vector<DotMap> pmaps(3 * (D + 1));
-  for (int g = 0; g <= D; ++g) dot_gap_pieces(g, D, sorted.data(), nleaves, &pieces[3 * g]);
   DotWork w{};
-  w.cta_maps = cta_maps.data(); w.leaf_maps = leaf_maps.data();
-  for (size_t pi = 0; pi < pieces.size(); ++pi) {
-    DotMap mm = dot_identity();
-    for (int i = pieces[pi].begin; i < pieces[pi].end; ++i) mm = dot_compose(mm, pieces[pi].kind == 0 ? leaf_maps[i] : cta_maps[i]);
-    pmaps[pi] = mm;
-    if (stats && pieces[pi].end > pieces[pi].begin && mm.hyp == HYP_INVALID) stats[2]++;
+  w.cta_maps = cta_maps.data(); w.leaf_maps = leaf_maps.data(); w.warp_maps = warp_maps.data(); w.super_maps = super_maps.data(); w.hyper_maps = hyper_maps.data();
+  double s = 0.0;
+  for (int g = 0; g <= D; ++g) {
+    const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
+    WalkPiece pc[DOT_GAP_PIECES];
+    dot_gap_decompose(lo, hi, pc);
+    DotMap gm = dot_identity();
+    long long covered = lo;
+    for (int q = 0; q < DOT_GAP_PIECES; ++q) {
+      if (pc[q].count > 0 && (long long)pc[q].begin * dot_level_size(pc[q].level) != covered && stats) stats[2] += 1000000;   // decomposition must tile [lo,hi)
+      for (int i = 0; i < pc[q].count; ++i) gm = dot_compose(gm, dot_level_maps(w, pc[q].level)[pc[q].begin + i]);
+      covered += (long long)pc[q].count * dot_level_size(pc[q].level);
+    }
+    if (covered != (lo < hi ? hi : lo) && stats) stats[2] += 1000000;
+    if (lo < hi && !dot_apply(gm, s)) { if (stats) stats[2]++; s = dot_walk_gap_slow(lo, hi, w, x, y, n, s); }
+    if (g < D) { const long long b = (long long)sorted[g] * DOT_LEAF, e = b + DOT_LEAF < n ? b + DOT_LEAF : n; s = dot_replay(x, y, b, e, s); }
   }
-  return dot_walk_final(D, sorted.data(), pieces.data(), pmaps.data(), w, x, y, n);
+  return s;
 }
 
 double hs_serial_dot(long long n, const double *x, const double *y) { return dot_replay(x, y, 0, n, 0.0); }
