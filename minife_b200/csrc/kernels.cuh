@@ -637,7 +637,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
   if (tid == 0) hyps[DOT_CTA_THREADS] = dot_hyp_of(w.chunk_prefix[blockIdx.x + 1]);
   __syncthreads();
   const int hyp_end = hyps[tid + 1];
-  DotMap m = dot_leaf_map_products_fp(mine, cnt, hyp);
+  DotMap m = dot_leaf_map_products_fast(mine, cnt, hyp);
   const bool dirty = cnt > 0 && (m.hyp == HYP_INVALID || hyp != hyp_end);
   const int any_dirty = __syncthreads_or(dirty ? 1 : 0);
   DotMap cmap;                                      // chunk map (valid on warp 0, lane 31)
@@ -757,23 +757,28 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
       const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
       WalkPiece pc[DOT_GAP_PIECES];
       dot_gap_decompose(lo, hi, pc);
-      DotMap pm[DOT_GAP_PIECES];
+      // the maps of the gap in application order form one flat list; lane l takes a contiguous slice of it
+      int total = 0;
 #pragma unroll
-      for (int q = 0; q < DOT_GAP_PIECES; ++q) {           // all loads first: one latency for the whole gap
-        pm[q] = dot_identity();
-        if (pc[q].count <= 32) { if (lane < pc[q].count) pm[q] = load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + lane); }
-        else {                                             // only the top level of very long vectors
-          const int per = (pc[q].count + 31) / 32, b = lane * per, e = min(pc[q].count, b + per);
-          for (int i = b; i < e; ++i) pm[q] = dot_compose(pm[q], load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + i));
-        }
-      }
+      for (int q = 0; q < DOT_GAP_PIECES; ++q) total += pc[q].count;
+      const int per = (total + 31) / 32, f0 = lane * per, f1 = min(total, f0 + per);
       DotMap gm = dot_identity();
+      for (int base = f0; base < f1; base += 8) {
+        DotMap buf[8];
 #pragma unroll
-      for (int q = 0; q < DOT_GAP_PIECES; ++q) {
-        if (pc[q].count == 0) continue;                    // warp-uniform
-        const DotMap r = warp_compose(pm[q], lane);
-        gm = dot_compose(gm, r);                           // meaningful on lane 31
+        for (int u = 0; u < 8; ++u) {
+          int f = base + u;
+          if (f < f1) {
+            int q = 0;
+#pragma unroll
+            for (int t = 0; t < DOT_GAP_PIECES - 1; ++t) if (q == t && f >= pc[t].count) { f -= pc[t].count; q = t + 1; }
+            buf[u] = load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (base + u < f1) gm = dot_compose(gm, buf[u]);
       }
+      gm = warp_compose(gm, lane);
       if (lane == 31) gmaps[g] = gm;
     }
     __syncthreads();

@@ -259,7 +259,7 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
     hyps[DOT_CTA_THREADS] = dot_hyp_of(chunk_prefix[c + 1]);
     DotMap lm[DOT_CTA_THREADS]; bool any = false; bool dl[DOT_CTA_THREADS];
     for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      lm[t] = dot_leaf_map_products_fp(prod[t], cnt[t], hyps[t]);
+      lm[t] = dot_leaf_map_products_fast(prod[t], cnt[t], hyps[t]);
       {   // the integer formulation must agree (offsets exactly; the fp bounds may only be wider) wherever usable
         const DotMap li = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
         const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && lm[t].lo <= li.lo && lm[t].hi >= li.hi && lm[t].lo >= li.lo - 16 && lm[t].hi <= li.hi + 16;
