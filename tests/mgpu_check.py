@@ -1,0 +1,104 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity check, one rank per GPU (run under torch.distributed.run; needs N GPUs):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tests/mgpu_check.py [--sizes 8x8x8,20x30x40,64x64x64]
+
+Every rank builds its share with minife_b200 (NCCL halo exchange + rank-ordered dot allgather) and compares with the
+CPU oracle run at the SAME number of ranks: CSR, index maps, exchange_externals, matvec, CG history and solution,
+all bit-exact.  Exit code 0 = all ranks agree."""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    import minife_b200 as mf
+    from oracle_lib import Oracle, EPS
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sizes", default="2x2x2,8x8x8,5x3x7,20x30x40,64x64x64")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    failures = []
+
+    def bits(a):
+        return np.ascontiguousarray(a, np.float64).view(np.int64)
+
+    def check(cond, what):
+        if not cond:
+            failures.append(what)
+            print("[rank %d] MISMATCH: %s" % (rank, what), flush=True)
+
+    for size in args.sizes.split(","):
+        n = tuple(int(v) for v in size.split("x"))
+        if min(n) * 1 < 1 or (n[0] * n[1] * n[2]) < world:
+            continue
+        gbox = mf.Box([0, n[0], 0, n[1], 0, n[2]])
+        boxes = mf.box_partition(0, world, 2, gbox)
+        if any((b.ranges[1] - b.ranges[0]) * (b.ranges[3] - b.ranges[2]) * (b.ranges[5] - b.ranges[4]) == 0 for b in boxes):
+            continue      # the reference itself refuses ranks without elements (main.cpp:116-130)
+        mesh = mf.simple_mesh_description(gbox, boxes[rank], rank=rank, nranks=world, all_boxes=boxes, device=local)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(mf.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        mesh.comm_init(bytes(idt.cpu().numpy().tobytes()))
+        A = mf.CSRMatrix()
+        mf.generate_matrix_structure(mesh, A)
+        b = mf.Vector(int(A.rows[0]), A.num_rows()); x = mf.Vector(int(A.rows[0]), A.num_rows())
+        mf.assemble_FE_data(mesh, A, b)
+        mf.impose_dirichlet(0.0, A, b, bc_rows=0); mf.impose_dirichlet(1.0, A, b, bc_rows=1)
+        mf.make_local_matrix(A)
+        o = Oracle(*n, world).setup()
+        rows, ro, cols, coefs = o.csr(rank)
+        check(np.array_equal(A.row_offsets, ro) and np.array_equal(A.packed_cols, cols), "%s CSR structure" % size)
+        check(np.array_equal(bits(A.packed_coefs), bits(coefs)) and np.array_equal(bits(b.coefs), bits(o.b(rank))), "%s A/b values" % size)
+        for m in ("external_index", "external_local_index", "elements_to_send", "neighbors", "recv_length", "send_length"):
+            check(np.array_equal(getattr(A, m), o.get_map(m, rank)), "%s %s" % (size, m))
+        # exchange_externals + matvec on a global pattern: x_global[row] = f(row)
+        ncols = A.num_cols
+        first = int(A.rows[0])
+        f = lambda r: np.sin(0.37 * r) + 1e-3 * r
+        xv = np.zeros(ncols); xv[:A.num_rows()] = f(first + np.arange(A.num_rows()))
+        want_ext = f(o.get_map("external_index", rank).astype(np.float64))
+        order = o.get_map("external_local_index", rank) - A.num_rows()
+        want_tail = np.zeros(ncols - A.num_rows()); want_tail[order] = want_ext
+        xe = xv.copy()
+        mf.exchange_externals(A, xe)
+        check(np.array_equal(bits(xe[A.num_rows():]), bits(want_tail)), "%s exchange_externals" % size)
+        y = np.zeros(A.num_rows())
+        mf.matvec(A, xv, y)
+        xo = xv.copy(); xo[A.num_rows():] = want_tail
+        check(np.array_equal(bits(y), bits(o.matvec(xo, rank))), "%s matvec" % size)
+        # free-running CG against the oracle at np = world
+        want = o.cg_solve(200, EPS)
+        iters, normr, times, h = mf.cg_solve(A, b, x, mf.matvec_std(), 200, EPS, history=True)
+        check(iters == want["num_iters"], "%s iterations %d vs %d" % (size, iters, want["num_iters"]))
+        k = min(iters, want["num_iters"])
+        check(np.array_equal(bits(h["normr"][:k + 1]), bits(want["normr"][:k + 1])), "%s residual history" % size)
+        check(np.array_equal(bits(x.coefs), bits(o.x(rank))), "%s solution" % size)
+        if rank == 0:
+            rel = np.abs(h["normr"][:k + 1] - want["normr"][:k + 1]) / np.maximum(want["normr"][:k + 1], 1e-300)
+            print("size %s np=%d: iters %d (oracle %d), final resid %.6g, max rel diff of history %.3g" % (size, world, iters, want["num_iters"], normr, rel.max()), flush=True)
+        mesh.close()
+    t = torch.tensor([len(failures)], device="cuda")
+    dist.all_reduce(t)
+    if rank == 0:
+        print("MGPU_CHECK %s (%d mismatches over %d ranks)" % ("OK" if int(t) == 0 else "FAILED", int(t), world), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0 if int(t) == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
