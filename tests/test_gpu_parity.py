@@ -290,3 +290,22 @@ def test_size_independent_properties_128(product_lib):
     # golden values of the reference at 128^3 (printed with 6 digits)
     assert abs(h["normr"][0] - 129.004) < 5e-4 and abs(h["normr"][20] - 0.0529612) < 5e-8
     assert abs(h["normr"][100] - 0.0036414) < 5e-8 and abs(normr - 1.13069e-05) < 5e-11
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_cg_history_equals_reference_golden_at_full_size(n, product_lib):
+    """BASELINE config 2 (256^3): the 200-iteration history of the UNMODIFIED reference (tests/golden/history_<n>.npz,
+    generated by tests/golden/make_golden.py from ref/src) is reproduced bit for bit -- residual norms, p.Ap and alpha
+    of every iteration -- and so is the solution (CRC)."""
+    import os, zlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "history_%d.npz" % n))
+    p = Problem(n, n, n).setup()
+    iters, normr, times, h = mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS, history=True)
+    assert iters == int(g["num_iters"]) == 200
+    assert_bits(h["normr"][1:], g["normr"][1:], "normr history vs reference")
+    assert_bits(h["pap"][1:], g["pap"][1:], "p.Ap history vs reference")
+    assert_bits(h["alpha"][1:], g["alpha"][1:], "alpha history vs reference")
+    assert_bits([normr], [float(g["final_normr"])], "final residual")
+    assert np.uint32(zlib.crc32(p.x.coefs.tobytes())) == g["crc_x"]
+    rel = np.abs(h["normr"][1:] - g["normr"][1:]) / g["normr"][1:]
+    assert rel.max() <= 1e-8      # the tolerance BASELINE.json states; we are at 0
