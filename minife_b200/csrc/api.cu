@@ -123,9 +123,10 @@ struct mfe_ctx {
   double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
   int dot_mode = MFE_DOT_EXACT;
   int op_timing = 1;
-  int mv_cfg = 9;                // SpMV configuration (see matvec_configs): 32 rows x 10 groups x 2 stages
+  int mv_cfg = 15;               // SpMV configuration (see matvec_configs): v2, 16 warps x 1 stage, 2 gather batches per row
   int tr = 32;                   // rows per SpMV tile of that configuration
   int mv_flags = MV_STREAM_HINT;
+  int mv_line_tiles = 0;         // v2 tile order: 0 natural order (fastest measured), -1 tiles per mesh x-line, > 0 explicit
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -527,6 +528,27 @@ static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, double *til
   return 0;
 }
 
+template <int G, int S, int H>
+static int launch_matvec2_cfg(mfe_ctx *c, const double *x, double *y, double *tile_sums, const CgScalars *gate, int k)
+{
+  static bool attr_set[64] = { false };
+  const size_t smem = (size_t)G * S * MatvecCfg<32>::SLOT_BYTES + (size_t)G * S * 8 + 64;
+  auto kern = k_matvec2<G, S, H>;
+  if (!attr_set[c->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[c->device & 63] = true;
+  }
+  int lt = c->mv_line_tiles;
+  if (lt < 0) lt = c->mesh_csr ? std::max(1, (c->m.lnx + 16) / 32) : 0;
+  if ((int64_t)lt * G * 4 > c->ntiles) lt = 0;             // tiny matrices: natural order
+  const int64_t nsuper = lt > 0 ? ((c->ntiles + (int64_t)G * lt - 1) / ((int64_t)G * lt)) * lt : (c->ntiles + G - 1) / G;
+  const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, nsuper));
+  kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, lt, 0,
+                                          tile_sums, gate, k);
+  c->launches++;
+  return 0;
+}
+
 // halo exchange on the context stream: ref/src/exchange_externals.hpp:44-161
 static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 {
@@ -547,7 +569,9 @@ static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 
 // SpMV configurations: rows per tile (= threads per group), groups per CTA, smem stages per group
 struct MvCfg { int tr, g, s; };
-static const MvCfg matvec_configs[] = { {64, 4, 2}, {64, 3, 3}, {32, 8, 2}, {128, 2, 2}, {64, 5, 2}, {32, 6, 3}, {32, 4, 5}, {64, 2, 4}, {128, 1, 4}, {32, 10, 2} };
+static const MvCfg matvec_configs[] = { {64, 4, 2}, {64, 3, 3}, {32, 8, 2}, {128, 2, 2}, {64, 5, 2}, {32, 6, 3}, {32, 4, 5}, {64, 2, 4}, {128, 1, 4}, {32, 10, 2},
+                                        /* 10.. : k_matvec2 (warp per tile; batches per row in the comment) */ {32, 10, 2}, {32, 12, 1}, {32, 14, 1}, {32, 20, 1}, {32, 18, 1},
+                                        {32, 16, 1} /*2*/, {32, 16, 1}, {32, 18, 1} /*2*/, {32, 20, 1} /*2*/, {32, 21, 1} /*2*/, {32, 21, 1} /*3*/, {32, 20, 1} /*3*/ };
 enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
 
 static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, double *sums, const CgScalars *gate, int k)
@@ -563,6 +587,18 @@ static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, double *s
     case 7: return launch_matvec_cfg<64, 2, 4>(c, x, y, sums, gate, k);
     case 8: return launch_matvec_cfg<128, 1, 4>(c, x, y, sums, gate, k);
     case 9: return launch_matvec_cfg<32, 10, 2>(c, x, y, sums, gate, k);
+    case 10: return launch_matvec2_cfg<10, 2, 1>(c, x, y, sums, gate, k);
+    case 11: return launch_matvec2_cfg<12, 1, 1>(c, x, y, sums, gate, k);
+    case 12: return launch_matvec2_cfg<14, 1, 1>(c, x, y, sums, gate, k);
+    case 13: return launch_matvec2_cfg<20, 1, 1>(c, x, y, sums, gate, k);
+    case 14: return launch_matvec2_cfg<18, 1, 1>(c, x, y, sums, gate, k);
+    case 15: return launch_matvec2_cfg<16, 1, 2>(c, x, y, sums, gate, k);
+    case 16: return launch_matvec2_cfg<16, 1, 1>(c, x, y, sums, gate, k);
+    case 17: return launch_matvec2_cfg<18, 1, 2>(c, x, y, sums, gate, k);
+    case 18: return launch_matvec2_cfg<20, 1, 2>(c, x, y, sums, gate, k);
+    case 19: return launch_matvec2_cfg<21, 1, 2>(c, x, y, sums, gate, k);
+    case 20: return launch_matvec2_cfg<21, 1, 3>(c, x, y, sums, gate, k);
+    case 21: return launch_matvec2_cfg<20, 1, 3>(c, x, y, sums, gate, k);
   }
   return fail("bad matvec configuration %d", c->mv_cfg);
 }
@@ -790,6 +826,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
     return 0;
   }
   if (!strcmp(name, "matvec_flags")) { c->mv_flags = (int)value; return 0; }
+  if (!strcmp(name, "matvec_line_tiles")) { c->mv_line_tiles = (int)value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
 
@@ -987,6 +1024,24 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
     if (!strcmp(what, "matvec")) return launch_matvec_local(c, c->d_p, c->d_Ap, nullptr, nullptr, 0);
     if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, c->d_p, c->d_Ap, c->d_tile_sums, nullptr, 0);
     if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n); c->launches++; return 0; }
+    if (!strcmp(what, "stream_probe")) {
+      constexpr int PG = 16, PS = 1;
+      const size_t smem = (size_t)PG * PS * MatvecCfg<32>::SLOT_BYTES + (size_t)PG * PS * 8 + 64;
+      auto kern = k_stream_probe<PG, PS>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return fail("stream_probe: smem attribute");
+      if (c->tr != 32) return fail("stream_probe needs a 32-row tile configuration");
+      kern<<<c->sm_count, 32 * PG, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_tile_base, c->ntiles, c->nnz_padded, c->d_tmp1);
+      c->launches++; return 0;
+    }
+    if (!strcmp(what, "stream_probe21")) {
+      constexpr int PG = 21, PS = 1;
+      const size_t smem = (size_t)PG * PS * MatvecCfg<32>::SLOT_BYTES + (size_t)PG * PS * 8 + 64;
+      auto kern = k_stream_probe<PG, PS>;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return fail("stream_probe: smem attribute");
+      if (c->tr != 32) return fail("stream_probe needs a 32-row tile configuration");
+      kern<<<c->sm_count, 32 * PG, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_tile_base, c->ntiles, c->nnz_padded, c->d_tmp1);
+      c->launches++; return 0;
+    }
     if (!strcmp(what, "waxpby")) { launch_waxpby(c, n, one, c->d_r, half, c->d_p, c->d_tmp1, nullptr, 0); return 0; }
     if (!strcmp(what, "dot_rr")) return launch_dot(c, n, c->d_r, c->d_r, 0, EPI_NONE, 0, false, nullptr);
     if (!strcmp(what, "dot_pap")) return launch_dot(c, n, c->d_Ap, c->d_p, 0, EPI_NONE, 0, false, nullptr);

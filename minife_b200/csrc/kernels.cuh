@@ -423,6 +423,219 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// SpMV v2 (default): one WARP per tile of 32 rows, G warps per CTA, S smem stages per warp, no runtime flags.
+// Same staging as k_matvec (two 1-D bulk copies per tile, matrix stream marked evict_first), but the consumer is
+// specialised: when every row of the tile holds exactly 27 entries (interior of the hex8 mesh: ~87 % of the
+// tiles at 256^3) the row walk has no predication at all -- per entry LDS.64 coef, LDS col, IMAD.WIDE, LDG x,
+// DMUL, DADD -- and any other staged tile uses predicated adds (the select stays off the dependent chain).
+// line_tiles > 0 permutes the tile order so that the G warps of a CTA walk G ADJACENT x-lines of the mesh in step:
+// the x entries of neighbouring lines are then shared through L1 instead of being re-fetched from L2.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dadd_if(double &sum, double prod, int u, int len)
+{
+  asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %2, %3;\n@p add.rn.f64 %0, %0, %1;\n}\n" : "+d"(sum) : "d"(prod), "r"(u), "r"(len));
+}
+
+template <int G, int S, int H>
+__global__ void __launch_bounds__(32 * G, 1)
+k_matvec2(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
+          const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
+          int64_t ntiles, int64_t nnz_padded, int line_tiles, int zmask, double *__restrict__ tile_sums, const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  constexpr int TR = 32;
+  constexpr int CAP = MatvecCfg<TR>::CAP;
+  constexpr int SLOT = MatvecCfg<TR>::SLOT_BYTES;
+  constexpr int U = 27;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *gbase = smem + (size_t)w * S * SLOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
+  uint64_t pol_stream = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+
+  // tile sequence of this warp: superstep q = blockIdx.x, blockIdx.x + gridDim.x, ...; tile_of(q) < 0: nothing there
+  const int64_t LT = line_tiles > 0 ? line_tiles : 1;
+  const int64_t band = (int64_t)G * LT;
+  const int64_t nsuper = line_tiles > 0 ? ((ntiles + band - 1) / band) * LT : (ntiles + G - 1) / G;
+  auto tile_of = [&](int64_t q) -> int64_t {
+    const int64_t t = line_tiles > 0 ? (q / LT) * band + (int64_t)w * LT + (q % LT) : q * G + w;
+    return t < ntiles ? t : -1;
+  };
+  auto next_valid = [&](int64_t &q) -> int64_t {      // advance q to the next superstep holding a tile for this warp
+    for (q += gridDim.x; q < nsuper; q += gridDim.x) { const int64_t t = tile_of(q); if (t >= 0) return t; }
+    return -1;
+  };
+  auto issue = [&](int64_t t, int s) {
+    const int64_t a0 = tile_base[t] & ~3LL;
+    int64_t a1 = (tile_base[t + 1] + 3) & ~3LL;
+    if (a1 > nnz_padded) a1 = nnz_padded;
+    const int64_t n = a1 - a0;
+    if (n <= 0 || n > CAP) return;                      // oversized tile: consumers read global memory directly
+    double *sc = reinterpret_cast<double *>(gbase + (size_t)s * SLOT);
+    int *si = reinterpret_cast<int *>(gbase + (size_t)s * SLOT + CAP * 8);
+    mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
+    bulk_g2s_hint(sc, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
+    bulk_g2s_hint(si, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  int64_t qc = (int64_t)blockIdx.x - gridDim.x;          // consume cursor (superstep), advanced by next_valid
+  int64_t t = next_valid(qc);
+  int64_t qi = qc, ti = t;                               // issue cursor, runs S tiles ahead
+  if (lane == 0)
+    for (int s = 0; s < S && ti >= 0; ++s) { issue(ti, s); ti = next_valid(qi); }
+  // (lanes other than 0 do not track the issue cursor)
+
+  uint32_t phase_bits = 0;
+  uint32_t o0n = 0, o1n = 0; int64_t tb0n = 0, tb1n = 0;
+  if (t >= 0) {
+    const int64_t r = t * TR + lane;
+    if (r < nrows) { o0n = roff[r]; o1n = roff[r + 1]; }
+    tb0n = tile_base[t]; tb1n = tile_base[t + 1];
+  }
+  for (int64_t j = 0; t >= 0; ++j) {
+    const int s = (int)(j % S);
+    const uint32_t parity = (phase_bits >> s) & 1u;
+    const int64_t r = t * TR + lane;
+    const uint32_t o0 = o0n, o1 = o1n;
+    const int64_t tb0 = tb0n, tb1 = tb1n;
+    int64_t qn = qc;
+    const int64_t tn = next_valid(qn);
+    if (tn >= 0) {
+      const int64_t rn = tn * TR + lane;
+      o0n = 0; o1n = 0;
+      if (rn < nrows) { o0n = roff[rn]; o1n = roff[rn + 1]; }
+      tb0n = tile_base[tn]; tb1n = tile_base[tn + 1];
+    }
+    const int64_t a0 = tb0 & ~3LL;
+    int64_t a1 = (tb1 + 3) & ~3LL;
+    if (a1 > nnz_padded) a1 = nnz_padded;
+    const int64_t ntile = a1 - a0;
+    const bool staged = ntile > 0 && ntile <= CAP;
+    const bool live = r < nrows;
+    const int len = live ? (int)(o1 - o0) : 0;
+    const bool full = staged && __all_sync(0xffffffffu, len == U);
+
+    double sum = 0.0;                 // beta*y with beta = 0 (SparseMatrix_functions.hpp:565-568)
+    const double xr = (tile_sums && live) ? __ldg(x + r) : 0.0;
+    if (staged) {
+      mbar_wait(&bars[s], parity);
+      phase_bits ^= 1u << s;
+      const double *sc = reinterpret_cast<const double *>(gbase + (size_t)s * SLOT);
+      const int *si = reinterpret_cast<const int *>(gbase + (size_t)s * SLOT + CAP * 8);
+      // first entry of this row inside the stage: 32-bit difference to the tile's first row + tile skew
+      const int base = (int)(uint32_t)(o0 - (uint32_t)tb0) + (int)(tb0 - a0);
+      if (full) {
+        // H batches of B entries: all gathers of a batch are in flight before its dependent add chain starts (see
+        // k_matvec: run-time-zero token).  H > 1 trades one extra gather latency per tile for fewer registers,
+        // i.e. more resident warps.
+        constexpr int B = (U + H - 1) / H;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          double cv[B], xv[B];
+#pragma unroll
+          for (int u = 0; u < B; ++u) if (h * B + u < U) { cv[u] = sc[base + h * B + u]; xv[u] = __ldg(x + si[base + h * B + u]); }
+          unsigned tok = 0;
+#pragma unroll
+          for (int u = 0; u < B; ++u) if (h * B + u < U) tok |= (unsigned)__double2hiint(xv[u]);
+          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+#pragma unroll
+          for (int u = 0; u < B; ++u) if (h * B + u < U) sum = __dadd_rn(sum, __dmul_rn(cv[u], xv[u]));
+        }
+      } else if (live) {
+        constexpr int B = (U + H - 1) / H;
+        for (int i0 = 0; i0 < len; i0 += B) {
+          double cv[B], xv[B];
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const int ii = (i0 + u < len) ? base + i0 + u : base;
+            cv[u] = sc[ii];
+            xv[u] = __ldg(x + si[ii]);
+          }
+          unsigned tok = 0;
+#pragma unroll
+          for (int u = 0; u < B; ++u) tok |= (unsigned)__double2hiint(xv[u]);
+          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+#pragma unroll
+          for (int u = 0; u < B; ++u) dadd_if(sum, __dmul_rn(cv[u], xv[u]), i0 + u, len);
+        }
+      }
+    } else if (live) {
+      const int64_t b0 = tb0 + (int64_t)(uint32_t)(o0 - (uint32_t)tb0);
+      for (int64_t i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[b0 + i], __ldg(x + cols[b0 + i])));
+    }
+    double prod = 0.0;
+    if (live) { y[r] = sum; prod = xr * sum; }
+    if (tile_sums) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) prod += __shfl_down_sync(0xffffffffu, prod, o);
+    }
+    __syncwarp();                     // every lane is done with stage s -> it can be refilled
+    if (lane == 0) {
+      if (tile_sums) tile_sums[t] = prod;
+      if (ti >= 0) { issue(ti, s); ti = next_valid(qi); }
+    }
+    qc = qn; t = tn;
+  }
+}
+
+// Streaming probe (measurement only): the staging half of k_matvec2 with the consumer removed -- every warp waits
+// for its tile and re-arms the stage at once.  Its GB/s is the ceiling of the TMA stream at this occupancy.
+template <int G, int S>
+__global__ void __launch_bounds__(32 * G, 1)
+k_stream_probe(const double *__restrict__ coefs, const int *__restrict__ cols, const int64_t *__restrict__ tile_base, int64_t ntiles,
+               int64_t nnz_padded, double *__restrict__ sink)
+{
+  constexpr int CAP = MatvecCfg<32>::CAP;
+  constexpr int SLOT = MatvecCfg<32>::SLOT_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *gbase = smem + (size_t)w * S * SLOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
+  uint64_t pol_stream = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  auto issue = [&](int64_t t, int s) -> bool {
+    const int64_t a0 = tile_base[t] & ~3LL;
+    int64_t a1 = (tile_base[t + 1] + 3) & ~3LL;
+    if (a1 > nnz_padded) a1 = nnz_padded;
+    const int64_t n = a1 - a0;
+    if (n <= 0 || n > CAP) return false;
+    mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
+    bulk_g2s_hint(gbase + (size_t)s * SLOT, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
+    bulk_g2s_hint(gbase + (size_t)s * SLOT + CAP * 8, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+    return true;
+  };
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (lane != 0) return;
+  const int64_t stride = (int64_t)gridDim.x * G;
+  int64_t t = (int64_t)blockIdx.x * G + w, ti = t;
+  unsigned armed = 0, phase_bits = 0;
+  for (int s = 0; s < S && ti < ntiles; ++s, ti += stride) if (issue(ti, s)) armed |= 1u << s;
+  double acc = 0.0;
+  for (int64_t j = 0; t < ntiles; ++j, t += stride) {
+    const int s = (int)(j % S);
+    if ((armed >> s) & 1u) {
+      mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
+      acc += *reinterpret_cast<const double *>(gbase + (size_t)s * SLOT);
+    }
+    armed &= ~(1u << s);
+    if (ti < ntiles) { if (issue(ti, s)) armed |= 1u << s; ti += stride; }
+  }
+  if (acc == 12345.678) *sink = acc;
+}
+
 // plain thread-per-row CSR SpMV in the reference order (validation twin of k_matvec; also any CSR import)
 __global__ void k_matvec_simple(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
                                 const int64_t *__restrict__ tile_base, int tr, const double *__restrict__ x, double *__restrict__ y,

@@ -11,7 +11,8 @@ ap.add_argument("--nx", type=int, default=256)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--configs", default="0,1,2,3,4,5,6,7,8,9")
 ap.add_argument("--iters", type=int, default=20)
-ap.add_argument("--flags", default="3")
+ap.add_argument("--flags", default="1")
+ap.add_argument("--line-tiles", default="-1")
 args = ap.parse_args()
 n = args.nx
 g = mf.Box([0, n, 0, n, 0, n])
@@ -28,12 +29,17 @@ for cfg in [int(c) for c in args.configs.split(",") if c != ""]:
     mesh.set_option("matvec_config", cfg)
     for fl in [int(f) for f in args.flags.split(",")]:
         mesh.set_option("matvec_flags", fl)
-        for what in ("matvec", "matvec_dot"):
-            ms = mesh.time_kernel(what, args.reps)
-            print(json.dumps({"kernel": what, "config": cfg, "flags": fl, "ms": ms, "GBs": mvb / ms / 1e6}))
-mesh.set_option("matvec_config", 4)
-mesh.set_option("matvec_flags", 3)
-for what, byts in (("matvec_simple", mvb), ("waxpby", 24.0 * N), ("xr_update", 48.0 * N), ("dot_rr", 8.0 * N), ("dot_pap", 16.0 * N)):
+        for lt in [int(v) for v in args.line_tiles.split(",")]:
+            if cfg < 10 and lt != int(args.line_tiles.split(",")[0]):
+                continue
+            mesh.set_option("matvec_line_tiles", lt)
+            for what in ("matvec", "matvec_dot"):
+                ms = mesh.time_kernel(what, args.reps)
+                print(json.dumps({"kernel": what, "config": cfg, "flags": fl, "line_tiles": lt, "ms": ms, "GBs": mvb / ms / 1e6}), flush=True)
+mesh.set_option("matvec_config", 10)
+mesh.set_option("matvec_flags", 1)
+mesh.set_option("matvec_line_tiles", -1)
+for what, byts in (("stream_probe", 12.0 * nnz), ("stream_probe21", 12.0 * nnz), ("matvec_simple", mvb), ("waxpby", 24.0 * N), ("xr_update", 48.0 * N), ("dot_rr", 8.0 * N), ("dot_pap", 16.0 * N)):
     for mode in ((0, 1, 2) if what.startswith("dot") else (0,)):
         if mode == 1 and n > 64:
             continue
