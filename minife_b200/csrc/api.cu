@@ -123,6 +123,7 @@ struct mfe_ctx {
   double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
   int dot_mode = MFE_DOT_EXACT;
   int op_timing = 1;
+  int dot_maps_ver = 2;          // exact-dot map kernel: 2 = register-resident leaves (default), 1 = shared-memory transposition
   int mv_cfg = 15;               // SpMV configuration (see matvec_configs): v2, 16 warps x 1 stage, 2 gather batches per row
   int tr = 32;                   // rows per SpMV tile of that configuration
   int mv_flags = MV_STREAM_HINT;
@@ -644,7 +645,12 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
       k_dot_tree_finish<<<1, 1, 0, c->stream>>>(w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
       c->launches++;
     } else {
-      if (nchunks > 0) { k_dot_maps<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k); c->launches++; }
+      if (nchunks > 0) {
+        if (c->dot_maps_ver == 1) k_dot_maps<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k);
+        else if (x == y) k_dot_maps2<true><<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k);
+        else k_dot_maps2<false><<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k);
+        c->launches++;
+      }
       k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
       c->launches++;
     }
@@ -827,6 +833,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   }
   if (!strcmp(name, "matvec_flags")) { c->mv_flags = (int)value; return 0; }
   if (!strcmp(name, "matvec_line_tiles")) { c->mv_line_tiles = (int)value; return 0; }
+  if (!strcmp(name, "dot_maps_version")) { if (value != 1 && value != 2) return fail("dot_maps_version must be 1 or 2"); c->dot_maps_ver = (int)value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
 

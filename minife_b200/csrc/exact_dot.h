@@ -254,37 +254,107 @@ MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
 // (FP64 min/max costs ~6 instructions on sm_100).  Anything else falls back to dot_leaf_map_products_fp.
 MFE_HD unsigned dot_hi32(double v) { return (unsigned)(MFE_D2U(v) >> 32); }
 
-MFE_HD DotMap dot_leaf_map_products_fast(const double *prod, int n, int hyp)
+// Full leaf (DOT_LEAF products), everything unrolled so that `prod` can live in registers on the device.
+MFE_HD DotMap dot_leaf_map16_fp(const double *prod, int hyp)
 {
-  if (n != DOT_LEAF || hyp < 0 || hyp == HYP_ZERO) return dot_leaf_map_products_fp(prod, n, hyp);
-  const int k = 1075 - (hyp & 0x7ff);
+  const int k = 1075 - (hyp & 0x7ff);                 // v = p * 2^k, k in [-971, 1074]
   const int k1 = k / 2, k2 = k - k1;
   const double c1 = dot_pow2(k1);
   const double c2 = ((hyp >> 11) & 1) ? -dot_pow2(k2) : dot_pow2(k2);
-  double A = 0.0, absum = 0.0, first = 0.0;
-  unsigned vmax = 0, dmax = 0;            // max of the high words of |v| and of |v - rint(v)| (monotone in the value)
+  double A0 = 0.0, A1 = 0.0, lo = 1.152921504606846976e18, hi = -1.152921504606846976e18, vmax = 0.0, nt = 0.0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-  for (int i = 0; i < DOT_LEAF; ++i) {
-    const double v = MFE_DMUL(MFE_DMUL(prod[i], c1), c2);
-    const double r = rint(v);
-    const double d = v - r;
-    A += r;
-    absum += fabs(r);
-    const unsigned hv = dot_hi32(v) & 0x7fffffffu, hd = dot_hi32(d) & 0x7fffffffu;
-    vmax = hv > vmax ? hv : vmax;
-    dmax = hd > dmax ? hd : dmax;
-    if (i == 0) first = r;
-  }
-  // |v| >= 2^52 / inf / nan  -> vmax >= 0x43300000 ; an exact tie |d| == 0.5 -> dmax == 0x3fe00000 (|d| <= 0.5 always)
-  const bool simple = vmax < 0x43300000u && dmax < 0x3fe00000u && absum == fabs(A);
-  if (!simple) return dot_leaf_map_products_fp(prod, n, hyp);
-  const double lo = A >= 0.0 ? first : A, hi = A >= 0.0 ? A : first;
-  if (!(lo > -4503599627370496.0 && hi < 4503599627370496.0)) return dot_invalid();
+  for (int i = 0; i < DOT_LEAF; ++i) MFE_DOT_FP_TERM(prod[i])
+  lo -= nt; hi += nt;
+  if (!(vmax < 4503599627370496.0) || !(A0 == A0) || !(A1 == A1) || !(lo > -4503599627370496.0 && hi < 4503599627370496.0))
+    return dot_invalid();
   DotMap m;
-  m.a0 = (long long)A; m.a1 = m.a0; m.lo = (long long)lo; m.hi = (long long)hi; m.hyp = hyp; m.pad = 0;
+  m.a0 = (long long)A0; m.a1 = (long long)A1; m.lo = (long long)lo; m.hi = (long long)hi; m.hyp = hyp; m.pad = 0;
   return m;
+}
+
+// The common leaf in "simple" form: no exact tie, so a0 == a1 = a = sum of the rounded offsets, whatever their signs.
+// Its bounds are CONSERVATIVE: every partial offset lies in [neg, pos], the sums of the negative / positive offsets
+// (order-independent, so the caller may visit the 16 products in any order).  Conservative bounds can only make
+// dot_apply reject a map whose running sum comes within one leaf's worth of offsets of a binade boundary, so they
+// are used only when the PREDICTED significand Sp = |pre| / ulp is farther than DOT_FAR_MARGIN ulps from both ends of
+// the binade; otherwise the function returns false and the caller takes the exact formulation
+// (dot_leaf_map16_fp).  A wrong prediction therefore costs time, never correctness.
+// Returns true and (a, lo, hi) as exact integers held in doubles.  Requires hyp >= 0 and hyp != HYP_ZERO.
+// |v| >= 2^52, inf and nan all surface in absum (= sum of |rint(v)|), so no per-term range check is needed.
+#define MFE_DOT_FAR_MARGIN 16777216.0   /* 2^24 ulps ~ 4e-9 relative; the prediction is good to ~1e-13 */
+MFE_HD bool dot_leaf16_simple(const double *prod, int hyp, double pre, double &a, double &lo, double &hi)
+{
+  const int k = 1075 - (hyp & 0x7ff);                 // v = p * 2^k, k in [-971, 1074]
+  const bool neg = ((hyp >> 11) & 1) != 0;
+  double A = 0.0, absum = 0.0, Sp;
+  unsigned dmax = 0;                                  // max high word of |v - rint(v)|: 0x3fe00000 <=> an exact tie
+  if (k <= 1023) {                                    // 2^k is a normal double: one exact scaling
+    const double c = neg ? -dot_pow2(k) : dot_pow2(k);
+    Sp = MFE_DMUL(pre, c);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < DOT_LEAF; ++i) {
+      const double v = MFE_DMUL(prod[i], c);
+      const double r = rint(v);
+      const double d = v - r;
+      A += r;
+      absum += fabs(r);
+      const unsigned hd = dot_hi32(d) & 0x7fffffffu;
+      dmax = hd > dmax ? hd : dmax;
+    }
+  } else {
+    const int k1 = k / 2, k2 = k - k1;
+    const double c1 = dot_pow2(k1);
+    const double c2 = neg ? -dot_pow2(k2) : dot_pow2(k2);
+    Sp = MFE_DMUL(MFE_DMUL(pre, c1), c2);
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < DOT_LEAF; ++i) {
+      const double v = MFE_DMUL(MFE_DMUL(prod[i], c1), c2);
+      const double r = rint(v);
+      const double d = v - r;
+      A += r;
+      absum += fabs(r);
+      const unsigned hd = dot_hi32(d) & 0x7fffffffu;
+      dmax = hd > dmax ? hd : dmax;
+    }
+  }
+  // absum < 2^52 bounds every |rint(v)|, |A|, pos and -neg (and rejects inf / nan)
+  if (!(dmax < 0x3fe00000u && absum < 4503599627370496.0)) return false;
+  const double pos = (absum + A) * 0.5, ng = (A - absum) * 0.5;     // exact: absum +- A are even integers < 2^53
+  const bool far = (Sp + ng) - MFE_DOT_FAR_MARGIN > 4503599627370496.0 && (Sp + pos) + MFE_DOT_FAR_MARGIN < 9007199254740992.0;
+  if (!far) return false;
+  a = A; lo = ng; hi = pos;
+  return true;
+}
+
+MFE_HD DotMap dot_leaf_map16(const double *prod, int hyp, double pre)
+{
+  if (hyp < 0) return dot_invalid();
+  if (hyp == HYP_ZERO) {
+    bool allz = true;
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+    for (int i = 0; i < DOT_LEAF; ++i) allz = allz && dot_is_zero(prod[i]);
+    return allz ? dot_zero_map() : dot_invalid();
+  }
+  double a, lo, hi;
+  if (!dot_leaf16_simple(prod, hyp, pre, a, lo, hi)) return dot_leaf_map16_fp(prod, hyp);
+  DotMap m;
+  m.a0 = (long long)a; m.a1 = m.a0; m.lo = (long long)lo; m.hi = (long long)hi; m.hyp = hyp; m.pad = 0;
+  return m;
+}
+
+// pre = predicted running sum at the start of the leaf (only steers the choice of formulation)
+MFE_HD DotMap dot_leaf_map_products_fast(const double *prod, int n, int hyp, double pre)
+{
+  if (n != DOT_LEAF) return dot_leaf_map_products_fp(prod, n, hyp);
+  return dot_leaf_map16(prod, hyp, pre);
 }
 
 // Apply a map to the running sum; false (s untouched) when the map does not provably reproduce the serial loop.

@@ -811,6 +811,48 @@ __device__ __forceinline__ DotMap warp_compose(DotMap m, int lane)
   return m;
 }
 
+// level 2 -> 3 -> 4 of the map hierarchy, called by warp 0 of a chunk with the chunk map on lane 31.
+__device__ __forceinline__ void dot_publish_chunk_map(const DotWork &w, const DotMap &cmap, int lane)
+{
+  // level 2 -> 3 -> 4: the last chunk of a group of 32 to arrive collapses the group (arrival tickets reset
+  // themselves, so the workspace is reusable without a memset)
+  const int c = blockIdx.x, nchunks = gridDim.x;
+  const int sgrp = c >> 5, ssize = min(32, nchunks - (sgrp << 5));
+  int last = 0;
+  if (lane == 31) {
+    w.cta_maps[c] = cmap;
+    __threadfence();
+    last = atomicAdd(&w.super_cnt[sgrp], 1) == ssize - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 31);
+  if (!last) return;
+  __threadfence();
+  DotMap sm = dot_identity();
+  if (lane < ssize) {
+    const DotMap *src = w.cta_maps + ((int64_t)sgrp << 5) + lane;
+    sm.a0 = __ldcg(&src->a0); sm.a1 = __ldcg(&src->a1); sm.lo = __ldcg(&src->lo); sm.hi = __ldcg(&src->hi); sm.hyp = __ldcg(&src->hyp); sm.pad = 0;
+  }
+  sm = warp_compose(sm, lane);
+  const int nsupers = (nchunks + 31) >> 5;
+  const int hgrp = sgrp >> 5, hsize = min(32, nsupers - (hgrp << 5));
+  if (lane == 31) {
+    w.super_maps[sgrp] = sm;
+    w.super_cnt[sgrp] = 0;
+    __threadfence();
+    last = atomicAdd(&w.hyper_cnt[hgrp], 1) == hsize - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 31);
+  if (!last) return;
+  __threadfence();
+  DotMap hm = dot_identity();
+  if (lane < hsize) {
+    const DotMap *src = w.super_maps + ((int64_t)hgrp << 5) + lane;
+    hm.a0 = __ldcg(&src->a0); hm.a1 = __ldcg(&src->a1); hm.lo = __ldcg(&src->lo); hm.hi = __ldcg(&src->hi); hm.hyp = __ldcg(&src->hyp); hm.pad = 0;
+  }
+  hm = warp_compose(hm, lane);
+  if (lane == 31) { w.hyper_maps[hgrp] = hm; w.hyper_cnt[hgrp] = 0; }
+}
+
 __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
                                                               DotWork w, const CgScalars *gate, int k)
 {
@@ -850,7 +892,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
   if (tid == 0) hyps[DOT_CTA_THREADS] = dot_hyp_of(w.chunk_prefix[blockIdx.x + 1]);
   __syncthreads();
   const int hyp_end = hyps[tid + 1];
-  DotMap m = dot_leaf_map_products_fast(mine, cnt, hyp);
+  DotMap m = dot_leaf_map_products_fast(mine, cnt, hyp, pre);
   const bool dirty = cnt > 0 && (m.hyp == HYP_INVALID || hyp != hyp_end);
   const int any_dirty = __syncthreads_or(dirty ? 1 : 0);
   DotMap cmap;                                      // chunk map (valid on warp 0, lane 31)
@@ -879,43 +921,138 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_dot_maps(int64_t n, const d
     }
   }
   if (warp != 0) return;
-  // level 2 -> 3 -> 4: the last chunk of a group of 32 to arrive collapses the group (arrival tickets reset
-  // themselves, so the workspace is reusable without a memset)
-  const int c = blockIdx.x, nchunks = gridDim.x;
-  const int sgrp = c >> 5, ssize = min(32, nchunks - (sgrp << 5));
-  int last = 0;
-  if (lane == 31) {
-    w.cta_maps[c] = cmap;
-    __threadfence();
-    last = atomicAdd(&w.super_cnt[sgrp], 1) == ssize - 1;
+  dot_publish_chunk_map(w, cmap, lane);
+}
+
+#ifndef DOT_MAPS_MIN_CTAS
+#define DOT_MAPS_MIN_CTAS 3
+#endif
+// Exact dot, map phase v2 (default).  Same maps as k_dot_maps, restructured for memory-level parallelism:
+// every thread fetches ITS leaf (16 consecutive terms = 128 contiguous bytes per operand) with 128-bit loads that
+// are all issued before the first use -- the 4 KB a warp touches are consumed whole through L1 -- the products
+// stay in registers (no shared-memory transposition), the leaf maps are collapsed per warp by ordered shuffles,
+// and only two block barriers remain (prefix of the leaf sums; the eight warp maps).
+template <bool SAME>
+__global__ void __launch_bounds__(DOT_CTA_THREADS, DOT_MAPS_MIN_CTAS) k_dot_maps2(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                                               DotWork w, const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  __shared__ double wtot[DOT_CTA_THREADS / 32];
+  __shared__ DotMap wmaps[DOT_CTA_THREADS / 32];
+  __shared__ int wdirty[DOT_CTA_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t base = (int64_t)blockIdx.x * DOT_CHUNK;
+  const int64_t lbeg = base + (int64_t)tid * DOT_LEAF;
+  const int cnt = (int)(lbeg >= n ? 0 : (n - lbeg < DOT_LEAF ? n - lbeg : DOT_LEAF));
+  const bool vec = cnt == DOT_LEAF && ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+  double prod[DOT_LEAF];
+  if (vec) {
+    const double2 *x2 = reinterpret_cast<const double2 *>(x + lbeg), *y2 = reinterpret_cast<const double2 *>(y + lbeg);
+    // products rounded once (fl(x*y)) exactly as the serial loop forms them
+    if (SAME) {
+      double2 xa[DOT_LEAF / 2];
+#pragma unroll
+      for (int q = 0; q < DOT_LEAF / 2; ++q) xa[q] = __ldg(x2 + q);
+#pragma unroll
+      for (int q = 0; q < DOT_LEAF / 2; ++q) { prod[2 * q] = __dmul_rn(xa[q].x, xa[q].x); prod[2 * q + 1] = __dmul_rn(xa[q].y, xa[q].y); }
+    } else {
+      double2 xa[DOT_LEAF / 2], ya[DOT_LEAF / 2];
+#pragma unroll
+      for (int q = 0; q < DOT_LEAF / 2; ++q) { xa[q] = __ldg(x2 + q); ya[q] = __ldg(y2 + q); }
+#pragma unroll
+      for (int q = 0; q < DOT_LEAF / 2; ++q) { prod[2 * q] = __dmul_rn(xa[q].x, ya[q].x); prod[2 * q + 1] = __dmul_rn(xa[q].y, ya[q].y); }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < DOT_LEAF; ++i) prod[i] = i < cnt ? __dmul_rn(__ldg(x + lbeg + i), __ldg(y + lbeg + i)) : 0.0;
   }
-  last = __shfl_sync(0xffffffffu, last, 31);
-  if (!last) return;
-  __threadfence();
-  DotMap sm = dot_identity();
-  if (lane < ssize) {
-    const DotMap *src = w.cta_maps + ((int64_t)sgrp << 5) + lane;
-    sm.a0 = __ldcg(&src->a0); sm.a1 = __ldcg(&src->a1); sm.lo = __ldcg(&src->lo); sm.hi = __ldcg(&src->hi); sm.hyp = __ldcg(&src->hyp); sm.pad = 0;
+  double ls = 0.0;
+#pragma unroll
+  for (int i = 0; i < DOT_LEAF; ++i) ls += prod[i];
+  // exclusive block scan of the leaf sums -> predicted running sum at the start of every leaf
+  double inc = ls;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+  if (lane == 31) wtot[warp] = inc;
+  const double cp0 = w.chunk_prefix[blockIdx.x], cp1 = w.chunk_prefix[blockIdx.x + 1];
+  __syncthreads();
+  double woff = 0.0, wmine = 0.0;
+#pragma unroll
+  for (int q = 0; q < DOT_CTA_THREADS / 32; ++q) { const double v = wtot[q]; if (q < warp) woff += v; if (q == warp) wmine = v; }
+  const double pre = cp0 + (woff + (inc - ls));
+  const int hyp = dot_hyp_of(pre);
+  // predicted binade at the start of the NEXT leaf (same expression the next thread evaluates for itself)
+  int hyp_end = __shfl_down_sync(0xffffffffu, hyp, 1);
+  if (lane == 31) hyp_end = warp == DOT_CTA_THREADS / 32 - 1 ? dot_hyp_of(cp1) : dot_hyp_of(cp0 + ((woff + wmine) + 0.0));
+  // leaf map: the common "simple" leaf (no tie, one sign) stays in floating point (a, lo, hi as exact integers in
+  // doubles); anything else gets the general int64 DotMap
+  bool simple = false;
+  double sa = 0.0, slo = 0.0, shi = 0.0;
+  DotMap m = dot_identity();
+  if (cnt == DOT_LEAF && hyp >= 0 && hyp != HYP_ZERO) {
+    simple = dot_leaf16_simple(prod, hyp, pre, sa, slo, shi);
+    if (!simple) m = dot_leaf_map16_fp(prod, hyp);
+  } else if (cnt == DOT_LEAF) {
+    m = dot_leaf_map16(prod, hyp, pre);                    // hyp < 0 or the running sum is exactly +0.0
+  } else if (cnt > 0) {
+    m = dot_leaf_map(x, y, lbeg, lbeg + cnt, hyp);         // ragged last leaf of the vector
   }
-  sm = warp_compose(sm, lane);
-  const int nsupers = (nchunks + 31) >> 5;
-  const int hgrp = sgrp >> 5, hsize = min(32, nsupers - (hgrp << 5));
-  if (lane == 31) {
-    w.super_maps[sgrp] = sm;
-    w.super_cnt[sgrp] = 0;
-    __threadfence();
-    last = atomicAdd(&w.hyper_cnt[hgrp], 1) == hsize - 1;
+  const bool dirty = cnt > 0 && ((!simple && m.hyp == HYP_INVALID) || hyp != hyp_end);
+  const int wd = __any_sync(0xffffffffu, dirty) ? 1 : 0;
+  // ordered collapse of the warp's 32 leaves onto lane 31
+  const int hyp0 = __shfl_sync(0xffffffffu, hyp, 0);
+  const bool all_simple = __all_sync(0xffffffffu, simple && hyp == hyp0);
+  DotMap wm;
+  if (all_simple) {
+    // simple maps compose in floating point: a = fa + ga, lo = min(flo, fa + glo), hi = max(fhi, fa + ghi); every
+    // value is an exact integer while below 2^53, and a map that ever exceeds 2^52 is unusable (checked below)
+    double ca = sa, clo = slo, chi = shi;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double fa = __shfl_up_sync(0xffffffffu, ca, o), flo = __shfl_up_sync(0xffffffffu, clo, o), fhi = __shfl_up_sync(0xffffffffu, chi, o);
+      if (lane >= o) {
+        const double nlo = fa + clo, nhi = fa + chi;
+        clo = flo < nlo ? flo : nlo;
+        chi = fhi > nhi ? fhi : nhi;
+        ca = fa + ca;
+      }
+    }
+    if (clo > -4503599627370496.0 && chi < 4503599627370496.0) {
+      wm.a0 = (long long)ca; wm.a1 = wm.a0; wm.lo = (long long)clo; wm.hi = (long long)chi; wm.hyp = hyp0; wm.pad = 0;
+    } else wm = dot_invalid();
+  } else {
+    if (simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
+    wm = warp_compose(m, lane);
   }
-  last = __shfl_sync(0xffffffffu, last, 31);
-  if (!last) return;
-  __threadfence();
-  DotMap hm = dot_identity();
-  if (lane < hsize) {
-    const DotMap *src = w.super_maps + ((int64_t)hgrp << 5) + lane;
-    hm.a0 = __ldcg(&src->a0); hm.a1 = __ldcg(&src->a1); hm.lo = __ldcg(&src->lo); hm.hi = __ldcg(&src->hi); hm.hyp = __ldcg(&src->hyp); hm.pad = 0;
+  if (lane == 31) { wmaps[warp] = wm; wdirty[warp] = wd; }
+  __syncthreads();
+  int any_dirty = 0;
+#pragma unroll
+  for (int q = 0; q < DOT_CTA_THREADS / 32; ++q) any_dirty |= wdirty[q];
+  DotMap cmap;                                      // chunk map (valid on warp 0, lane 31)
+  if (any_dirty) {
+    // dirty chunk: keep the leaf maps and the 8 warp maps so that the walker can stitch around the dirty leaves
+    if (simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
+    w.leaf_maps[(int64_t)blockIdx.x * DOT_CTA_THREADS + tid] = m;
+    if (dirty) {
+      const int slot = atomicAdd(w.dirty_count, 1);
+      if (slot < DOT_MAX_DIRTY) w.dirty_list[slot] = blockIdx.x * DOT_CTA_THREADS + tid;
+    }
+    if (lane == 31) w.warp_maps[(int64_t)blockIdx.x * (DOT_CTA_THREADS / 32) + warp] = wm;
+    cmap = dot_invalid();
+    cmap.pad = 1;
+  } else if (warp == 0) {
+    // the 8 warp maps sit on lanes 24..31; three ordered steps leave their composition on lane 31
+    constexpr int NWM = DOT_CTA_THREADS / 32;
+    cmap = lane >= 32 - NWM ? wmaps[lane - (32 - NWM)] : dot_identity();
+#pragma unroll
+    for (int o = 1; o < NWM; o <<= 1) {
+      const DotMap u = shfl_up_map(cmap, o);
+      if (lane >= o) cmap = dot_compose(u, cmap);
+    }
   }
-  hm = warp_compose(hm, lane);
-  if (lane == 31) { w.hyper_maps[hgrp] = hm; w.hyper_cnt[hgrp] = 0; }
+  if (warp != 0) return;
+  dot_publish_chunk_map(w, cmap, lane);
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -242,7 +242,7 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
       ls[t] = s;
     }
     // block scan as in the kernel: warp-inclusive (Hillis-Steele), then sequential warp offsets
-    double inc[DOT_CTA_THREADS], wtot[DOT_CTA_THREADS / 32];
+    double inc[DOT_CTA_THREADS], wtot[DOT_CTA_THREADS / 32], pres[DOT_CTA_THREADS];
     for (int w = 0; w < DOT_CTA_THREADS / 32; ++w) {
       double v[32];
       for (int l = 0; l < 32; ++l) v[l] = ls[w * 32 + l];
@@ -254,15 +254,17 @@ double hs_exact_dot(long long n, const double *x, const double *y, long long *st
       double woff = 0.0;
       for (int q = 0; q < t / 32; ++q) woff += wtot[q];
       const double pre = chunk_prefix[c] + (woff + (inc[t] - ls[t]));
+      pres[t] = pre;
       hyps[t] = dot_hyp_of(pre);
     }
     hyps[DOT_CTA_THREADS] = dot_hyp_of(chunk_prefix[c + 1]);
     DotMap lm[DOT_CTA_THREADS]; bool any = false; bool dl[DOT_CTA_THREADS];
     for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      lm[t] = dot_leaf_map_products_fast(prod[t], cnt[t], hyps[t]);
-      {   // the integer formulation must agree (offsets exactly; the fp bounds may only be wider) wherever usable
+      lm[t] = dot_leaf_map_products_fast(prod[t], cnt[t], hyps[t], pres[t]);
+      {   // the integer formulation must agree (offsets exactly; the fp bounds may only be wider: they are the sums of the
+          // negative / positive offsets when the leaf is far from a binade boundary) wherever usable
         const DotMap li = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
-        const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && lm[t].lo <= li.lo && lm[t].hi >= li.hi && lm[t].lo >= li.lo - 16 && lm[t].hi <= li.hi + 16;
+        const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && lm[t].lo <= li.lo && lm[t].hi >= li.hi;
         const bool int_unusable = li.hyp >= 0 && li.hyp != HYP_ZERO && (li.hi >= (1LL << 52) - 16 || li.lo <= -(1LL << 52) + 16 || li.hi - li.lo >= (1LL << 52) - 2);
         if (!same && !(lm[t].hyp == HYP_INVALID && int_unusable) && stats) { stats[3]++; if (getenv("HS_DEBUG")) fprintf(stderr, "leaf %d cnt %d hyp %d: int(%d %lld %lld %lld %lld) fp(%d %lld %lld %lld %lld)\n", t, cnt[t], hyps[t], li.hyp, li.a0, li.a1, li.lo, li.hi, lm[t].hyp, lm[t].a0, lm[t].a1, lm[t].lo, lm[t].hi); }
       }
