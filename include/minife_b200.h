@@ -73,7 +73,8 @@ int mfe_cg_solve(mfe_ctx *ctx, double *x_host, int max_iter, double tolerance, i
 int mfe_set_dot_mode(mfe_ctx *ctx, int mode);
 /* tuning knobs: "matvec_config" = index into the SpMV (rows-per-tile, groups, stages) table */
 int mfe_set_option(mfe_ctx *ctx, const char *name, int64_t value);
-/* 1: record per-op-class CUDA events to fill cg_times[WAXPY,DOT,MATVEC] (default), 0: only TOTAL */
+/* CUDA events inside mfe_cg_solve: 1 = around every op class, filling cg_times[WAXPY,DOT,MATVEC] (default);
+ * 2 = around the SpMV only (two events per iteration: cg_times[MATVEC]); 0 = none (only TOTAL) */
 int mfe_set_op_timing(mfe_ctx *ctx, int enabled);
 
 /* kernel-level entry points on HOST buffers (H2D + kernel + D2H inside the call) -- used by parity tests and

@@ -13,6 +13,8 @@
 
 #include "../../include/minife_b200.h"
 #include "kernels.cuh"
+#include "spmv.cuh"
+#include "dot_kernels.cuh"
 #include "halo_maps.h"
 
 using namespace mfe;
@@ -78,11 +80,10 @@ static int nccl_load()
 // ---------------------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------------------
-enum { MV_TR_MAX = 128 };       // largest rows-per-tile of any SpMV configuration (tile rows must divide DOT_CHUNK)
-
-struct DotWs {                  // workspace of one exact dot (sized for nrows)
-  DotWork w{};
-  double *chunk_tmp = nullptr;
+struct DotWs {                  // workspace of the exact dot (sized for nrows)
+  DotWork w{};                  // w.chunk_sums / w.piece_sums are set per launch to one of the two pairs below
+  double *chunk_sums_a = nullptr, *piece_sums_a = nullptr;   // written by k_xr_update (r.r) and k_chunk_sums
+  double *chunk_sums_b = nullptr, *piece_sums_b = nullptr;   // accumulated by the SpMV (p.Ap), zeroed by k_xr_update
 };
 
 struct mfe_ctx {
@@ -118,16 +119,13 @@ struct mfe_ctx {
   CgScalars *d_sc = nullptr;
   double *d_hist = nullptr;      // 4 * (max_iter+1)
   int hist_cap = 0;
-  double *d_tile_sums = nullptr; // ntiles
   DotWs dot;
   double *d_gather = nullptr;    // nranks doubles (allgather of local dots)
   int dot_mode = MFE_DOT_EXACT;
   int op_timing = 1;
-  int dot_maps_ver = 2;          // exact-dot map kernel: 2 = register-resident leaves (default), 1 = shared-memory transposition
-  int mv_cfg = 15;               // SpMV configuration (see matvec_configs): v2, 16 warps x 1 stage, 2 gather batches per row
-  int tr = 32;                   // rows per SpMV tile of that configuration
-  int mv_flags = MV_STREAM_HINT;
-  int mv_line_tiles = 0;         // v2 tile order: 0 natural order (fastest measured), -1 tiles per mesh x-line, > 0 explicit
+  int mv_cfg = 0;                // SpMV configuration (see matvec_configs): 16 warps x 1 stage, 2 gather batches per row
+  int tr = MV_TILE_ROWS;         // rows per SpMV tile
+  int dot_maps_warps = 0;        // warps per CTA of k_dot_maps: 0 = default (24), else 16 or 24
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -259,10 +257,11 @@ static void free_matrix(mfe_ctx *c)
 static void free_vectors(mfe_ctx *c)
 {
   free_dev(c->d_b); free_dev(c->d_x); free_dev(c->d_r); free_dev(c->d_p); free_dev(c->d_Ap); free_dev(c->d_tmp1); free_dev(c->d_tmp2);
-  free_dev(c->d_tile_sums); free_dev(c->dot.w.chunk_sums); free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps);
+  free_dev(c->dot.chunk_sums_a); free_dev(c->dot.piece_sums_a); free_dev(c->dot.chunk_sums_b); free_dev(c->dot.piece_sums_b);
+  free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps); free_dev(c->dot.w.chunk_cnt);
   free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.warp_maps); free_dev(c->dot.w.super_maps); free_dev(c->dot.w.hyper_maps);
-  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.chunk_tmp);
-  c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = c->d_tile_sums = nullptr;
+  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result);
+  c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = nullptr;
   c->dot = DotWs();
   c->vec_cap = 0;
 }
@@ -323,17 +322,21 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
     CK(cudaStreamSynchronize(c->stream));
   }
   free_dev(ob); free_dev(ox);
-  const int64_t nchunks = (need + DOT_CHUNK - 1) / DOT_CHUNK;
-  const int64_t ntiles = (need + 31) / 32;
-  if (dev_alloc(&c->d_tile_sums, ntiles + 1) || dev_alloc(&c->dot.w.chunk_sums, nchunks + 1) || dev_alloc(&c->dot.w.chunk_prefix, nchunks + 2) ||
+  const int64_t nchunks = (need + DOT_CHUNK - 1) / DOT_CHUNK, npieces = nchunks * DOT_PIECES_PER_CHUNK;
+  if (dev_alloc(&c->dot.chunk_sums_a, nchunks + 1) || dev_alloc(&c->dot.piece_sums_a, npieces + 1) || dev_alloc(&c->dot.chunk_sums_b, nchunks + 1) ||
+      dev_alloc(&c->dot.piece_sums_b, npieces + 1) || dev_alloc(&c->dot.w.chunk_prefix, nchunks + 2) ||
       dev_alloc(&c->dot.w.cta_maps, nchunks + 1) || dev_alloc(&c->dot.w.leaf_maps, (nchunks + 1) * DOT_CTA_THREADS) ||
-      dev_alloc(&c->dot.w.warp_maps, (nchunks + 1) * (DOT_CTA_THREADS / 32)) || dev_alloc(&c->dot.w.super_maps, nchunks / 32 + 2) ||
-      dev_alloc(&c->dot.w.hyper_maps, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.super_cnt, nchunks / 32 + 2) || dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) ||
-      dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) || dev_alloc(&c->dot.w.result, 1) ||
-      dev_alloc(&c->dot.chunk_tmp, nchunks + 1)) return 1;
+      dev_alloc(&c->dot.w.warp_maps, npieces + 8) || dev_alloc(&c->dot.w.super_maps, nchunks / 32 + 2) ||
+      dev_alloc(&c->dot.w.hyper_maps, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.chunk_cnt, nchunks + 1) || dev_alloc(&c->dot.w.super_cnt, nchunks / 32 + 2) ||
+      dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) ||
+      dev_alloc(&c->dot.w.result, 1)) return 1;
   CK(cudaMemsetAsync(c->dot.w.dirty_count, 0, sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->dot.w.chunk_cnt, 0, sizeof(int) * (nchunks + 1), c->stream));
   CK(cudaMemsetAsync(c->dot.w.super_cnt, 0, sizeof(int) * (nchunks / 32 + 2), c->stream));
   CK(cudaMemsetAsync(c->dot.w.hyper_cnt, 0, sizeof(int) * (nchunks / 1024 + 2), c->stream));
+  CK(cudaMemsetAsync(c->dot.chunk_sums_b, 0, 8 * (nchunks + 1), c->stream));
+  CK(cudaMemsetAsync(c->dot.piece_sums_b, 0, 8 * (npieces + 1), c->stream));
+  c->dot.w.chunk_sums = c->dot.chunk_sums_a; c->dot.w.piece_sums = c->dot.piece_sums_a;
   c->vec_cap = need;
   return 0;
 }
@@ -511,43 +514,43 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
 // ---------------------------------------------------------------------------------------------------------
 // kernels launchers
 // ---------------------------------------------------------------------------------------------------------
-template <int TR, int G, int S>
-static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, double *tile_sums, const CgScalars *gate, int k)
+// SpMV configurations: warps per CTA (= tiles in flight per SM), smem stages per warp, gather batches per row
+struct MvCfg { int g, s, h; };
+static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {12, 1, 1}, {14, 1, 1}, {18, 1, 2}, {20, 1, 2}, {21, 1, 2}, {21, 1, 3}, {20, 1, 3} };
+enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
+
+template <int G, int S, int H>
+static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k)
 {
   static bool attr_set[64] = { false };
-  const size_t smem = (size_t)G * S * MatvecCfg<TR>::SLOT_BYTES + (size_t)G * S * 8 + (size_t)G * 2 * (TR / 32) * 8 + 64;
-  auto kern = k_matvec<TR, G, S>;
+  const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 64;
+  auto kern = k_matvec<G, S, H>;
   if (!attr_set[c->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[c->device & 63] = true;
   }
-  const int64_t groups_needed = c->ntiles;
-  int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (groups_needed + G - 1) / G));
-  kern<<<grid, TR * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded,
-                                          c->num_cols > 0 ? c->num_cols : c->nrows, c->mv_flags, 0, tile_sums, gate, k);
+  const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (c->ntiles + G - 1) / G));
+  kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, 0,
+                                          with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k);
   c->launches++;
   return 0;
 }
 
-template <int G, int S, int H>
-static int launch_matvec2_cfg(mfe_ctx *c, const double *x, double *y, double *tile_sums, const CgScalars *gate, int k)
+static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k)
 {
-  static bool attr_set[64] = { false };
-  const size_t smem = (size_t)G * S * MatvecCfg<32>::SLOT_BYTES + (size_t)G * S * 8 + 64;
-  auto kern = k_matvec2<G, S, H>;
-  if (!attr_set[c->device & 63]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[c->device & 63] = true;
+  switch (c->mv_cfg) {
+    case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k);
+    case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k);
+    case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k);
+    case 3: return launch_matvec_cfg<12, 1, 1>(c, x, y, with_sums, gate, k);
+    case 4: return launch_matvec_cfg<14, 1, 1>(c, x, y, with_sums, gate, k);
+    case 5: return launch_matvec_cfg<18, 1, 2>(c, x, y, with_sums, gate, k);
+    case 6: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k);
+    case 7: return launch_matvec_cfg<21, 1, 2>(c, x, y, with_sums, gate, k);
+    case 8: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k);
+    case 9: return launch_matvec_cfg<20, 1, 3>(c, x, y, with_sums, gate, k);
   }
-  int lt = c->mv_line_tiles;
-  if (lt < 0) lt = c->mesh_csr ? std::max(1, (c->m.lnx + 16) / 32) : 0;
-  if ((int64_t)lt * G * 4 > c->ntiles) lt = 0;             // tiny matrices: natural order
-  const int64_t nsuper = lt > 0 ? ((c->ntiles + (int64_t)G * lt - 1) / ((int64_t)G * lt)) * lt : (c->ntiles + G - 1) / G;
-  const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, nsuper));
-  kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, lt, 0,
-                                          tile_sums, gate, k);
-  c->launches++;
-  return 0;
+  return fail("bad matvec configuration %d", c->mv_cfg);
 }
 
 // halo exchange on the context stream: ref/src/exchange_externals.hpp:44-161
@@ -568,46 +571,10 @@ static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
   return 0;
 }
 
-// SpMV configurations: rows per tile (= threads per group), groups per CTA, smem stages per group
-struct MvCfg { int tr, g, s; };
-static const MvCfg matvec_configs[] = { {64, 4, 2}, {64, 3, 3}, {32, 8, 2}, {128, 2, 2}, {64, 5, 2}, {32, 6, 3}, {32, 4, 5}, {64, 2, 4}, {128, 1, 4}, {32, 10, 2},
-                                        /* 10.. : k_matvec2 (warp per tile; batches per row in the comment) */ {32, 10, 2}, {32, 12, 1}, {32, 14, 1}, {32, 20, 1}, {32, 18, 1},
-                                        {32, 16, 1} /*2*/, {32, 16, 1}, {32, 18, 1} /*2*/, {32, 20, 1} /*2*/, {32, 21, 1} /*2*/, {32, 21, 1} /*3*/, {32, 20, 1} /*3*/ };
-enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
-
-static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, double *sums, const CgScalars *gate, int k)
-{
-  switch (c->mv_cfg) {
-    case 0: return launch_matvec_cfg<64, 4, 2>(c, x, y, sums, gate, k);
-    case 1: return launch_matvec_cfg<64, 3, 3>(c, x, y, sums, gate, k);
-    case 2: return launch_matvec_cfg<32, 8, 2>(c, x, y, sums, gate, k);
-    case 3: return launch_matvec_cfg<128, 2, 2>(c, x, y, sums, gate, k);
-    case 4: return launch_matvec_cfg<64, 5, 2>(c, x, y, sums, gate, k);
-    case 5: return launch_matvec_cfg<32, 6, 3>(c, x, y, sums, gate, k);
-    case 6: return launch_matvec_cfg<32, 4, 5>(c, x, y, sums, gate, k);
-    case 7: return launch_matvec_cfg<64, 2, 4>(c, x, y, sums, gate, k);
-    case 8: return launch_matvec_cfg<128, 1, 4>(c, x, y, sums, gate, k);
-    case 9: return launch_matvec_cfg<32, 10, 2>(c, x, y, sums, gate, k);
-    case 10: return launch_matvec2_cfg<10, 2, 1>(c, x, y, sums, gate, k);
-    case 11: return launch_matvec2_cfg<12, 1, 1>(c, x, y, sums, gate, k);
-    case 12: return launch_matvec2_cfg<14, 1, 1>(c, x, y, sums, gate, k);
-    case 13: return launch_matvec2_cfg<20, 1, 1>(c, x, y, sums, gate, k);
-    case 14: return launch_matvec2_cfg<18, 1, 1>(c, x, y, sums, gate, k);
-    case 15: return launch_matvec2_cfg<16, 1, 2>(c, x, y, sums, gate, k);
-    case 16: return launch_matvec2_cfg<16, 1, 1>(c, x, y, sums, gate, k);
-    case 17: return launch_matvec2_cfg<18, 1, 2>(c, x, y, sums, gate, k);
-    case 18: return launch_matvec2_cfg<20, 1, 2>(c, x, y, sums, gate, k);
-    case 19: return launch_matvec2_cfg<21, 1, 2>(c, x, y, sums, gate, k);
-    case 20: return launch_matvec2_cfg<21, 1, 3>(c, x, y, sums, gate, k);
-    case 21: return launch_matvec2_cfg<20, 1, 3>(c, x, y, sums, gate, k);
-  }
-  return fail("bad matvec configuration %d", c->mv_cfg);
-}
-
 static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k)
 {
   if (exchange(c, x, gate, k)) return 1;
-  return launch_matvec_local(c, x, y, with_sums ? c->d_tile_sums : nullptr, gate, k);
+  return launch_matvec_local(c, x, y, with_sums, gate, k);
 }
 
 static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, ScalarArg b, const double *y, double *w, const CgScalars *gate, int k)
@@ -618,9 +585,39 @@ static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, S
   c->launches++;
 }
 
+template <bool SAME, int NW>
+static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
+{
+  static bool attr_set[64] = { false };
+  const size_t smem = DotMapsCfg<SAME, NW>::SMEM_BYTES;
+  auto kern = k_dot_maps<SAME, NW>;
+  if (!attr_set[c->device & 63]) {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[c->device & 63] = true;
+  }
+  const int64_t npieces = (n + DOT_PIECE - 1) / DOT_PIECE;
+  if (npieces == 0) return 0;
+  // one persistent CTA per SM owning a contiguous range of pieces (more CTAs only when a range would overflow the table)
+  int64_t grid = std::min<int64_t>(c->sm_count, npieces);
+  grid = std::max<int64_t>(grid, (npieces + DOT_MAPS_MAX_PP - 1) / DOT_MAPS_MAX_PP);
+  const int PP = (int)((npieces + grid - 1) / grid);
+  grid = (npieces + PP - 1) / PP;
+  kern<<<(unsigned)grid, 32 * NW, smem, c->stream>>>(n, x, y, w, (int)npieces, PP, gate, k);
+  c->launches++;
+  return 0;
+}
+
+static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
+{
+  if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail("dot: operands must be 16-byte aligned");
+  const int nw = c->dot_maps_warps ? c->dot_maps_warps : 24;
+  if (x == y) return nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k);
+  return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k);
+}
+
 // local dot of x,y (n terms) + rank-ordered global sum + CG scalar epilogue.
-// sums_kind: 0 = none available (compute chunk sums here), 1 = chunk_sums already filled (k_xr_update),
-//            2 = SpMV tile sums available in d_tile_sums
+// sums_kind: where the prediction sums come from: 0 = nowhere yet (k_chunk_sums here), 1 = k_xr_update (pair a),
+//            2 = the SpMV (pair b)
 static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, int sums_kind, int epi, int k, bool gated, double *hist)
 {
   const CgScalars *gate = gated ? c->d_sc : nullptr;
@@ -629,29 +626,21 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
   const int nchunks = (int)((n + DOT_CHUNK - 1) / DOT_CHUNK);
   const bool multi = c->nranks > 1;
   const int epi_local = multi ? EPI_NONE : epi;
-  DotWork &w = c->dot.w;
+  DotWork w = c->dot.w;
+  w.chunk_sums = sums_kind == 2 ? c->dot.chunk_sums_b : c->dot.chunk_sums_a;
+  w.piece_sums = sums_kind == 2 ? c->dot.piece_sums_b : c->dot.piece_sums_a;
   if (c->dot_mode == MFE_DOT_SERIAL) {
     k_dot_serial<<<1, 1, 0, c->stream>>>(n, x, y, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
     c->launches++;
   } else {
-    if (sums_kind == 0) { if (nchunks > 0) { k_chunk_sums<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w.chunk_sums, gate, k); c->launches++; } }
-    if (sums_kind == 2 && nchunks > 0) {
-      k_tiles_to_chunks<<<grid_for(nchunks, 8), 256, 0, c->stream>>>(c->d_tile_sums, DOT_CHUNK / c->tr, (n + c->tr - 1) / c->tr, nchunks, w.chunk_sums, gate, k);
-      c->launches++;
-    }
-    k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, 1, nchunks, nchunks, c->dot.chunk_tmp, w.chunk_prefix, gate, k);
-    c->launches++;
+    if (sums_kind == 0 && nchunks > 0) { k_chunk_sums<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w.piece_sums, w.chunk_sums, gate, k); c->launches++; }
     if (c->dot_mode == MFE_DOT_TREE) {
+      k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, nchunks, w.chunk_prefix, gate, k);
       k_dot_tree_finish<<<1, 1, 0, c->stream>>>(w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
-      c->launches++;
+      c->launches += 2;
     } else {
-      if (nchunks > 0) {
-        if (c->dot_maps_ver == 1) k_dot_maps<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k);
-        else if (x == y) k_dot_maps2<true><<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k);
-        else k_dot_maps2<false><<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w, gate, k);
-        c->launches++;
-      }
-      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, nchunks, sc, epi_local, k, nh, rh, ph, ah, gate);
+      if (launch_dot_maps(c, n, x, y, w, gate, k)) return 1;
+      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, sc, epi_local, k, nh, rh, ph, ah, gate);
       c->launches++;
     }
   }
@@ -669,10 +658,11 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
 // ---------------------------------------------------------------------------------------------------------
 struct OpTimer {          // CUDA-event pairs per op class, resolved after the solve (no host sync inside)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
-  cudaStream_t s; bool on;
-  OpTimer(cudaStream_t st, bool enabled) : s(st), on(enabled) {}
-  void begin(int cls) { if (!on) return; cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); ev[cls].push_back({ a, b }); }
-  void end(int cls) { if (!on) return; cudaEventRecord(ev[cls].back().second, s); }
+  cudaStream_t s; int mode;      // 0: none, 1: every op class, 2: MATVEC only (two events per iteration)
+  OpTimer(cudaStream_t st, int m) : s(st), mode(m) {}
+  bool on(int cls) const { return mode == 1 || (mode == 2 && cls == MFE_MATVEC); }
+  void begin(int cls) { if (!on(cls)) return; cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); ev[cls].push_back({ a, b }); }
+  void end(int cls) { if (!on(cls)) return; cudaEventRecord(ev[cls].back().second, s); }
   double total_s(int cls) {
     double t = 0;
     for (auto &p : ev[cls]) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); t += ms; cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
@@ -720,8 +710,13 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   CK(cudaMemsetAsync(c->d_r, 0, n * 8, c->stream));
   CK(cudaMemsetAsync(c->d_p, 0, c->num_cols * 8, c->stream));
   CK(cudaMemsetAsync(c->d_Ap, 0, n * 8, c->stream));
+  {   // the SpMV accumulates its p.Ap prediction sums into pair b; k_xr_update re-zeroes them every iteration
+    const int64_t nch = (n + DOT_CHUNK - 1) / DOT_CHUNK;
+    CK(cudaMemsetAsync(c->dot.chunk_sums_b, 0, 8 * (nch + 1), c->stream));
+    CK(cudaMemsetAsync(c->dot.piece_sums_b, 0, 8 * (nch * DOT_PIECES_PER_CHUNK + 1), c->stream));
+  }
 
-  OpTimer ot(c->stream, c->op_timing != 0);
+  OpTimer ot(c->stream, c->op_timing);
   const ScalarArg one{ nullptr, 1.0 }, zero{ nullptr, 0.0 }, neg_one{ nullptr, -1.0 };
   CgScalars *sc = c->d_sc;
   double *hist = c->d_hist;
@@ -749,7 +744,8 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
       }
       resume_phase = 0;
       ot.begin(MFE_WAXPY);                                                                                               // (:211-212)
-      k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.w.chunk_sums, sc, k);
+      k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.piece_sums_a, c->dot.chunk_sums_a,
+                                                                             c->dot.piece_sums_b, c->dot.chunk_sums_b, sc, k);
       c->launches++;
       ot.end(MFE_WAXPY);
     }
@@ -823,17 +819,14 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   if (!c || !name) return fail("mfe_set_option: bad arguments");
   if (!strcmp(name, "matvec_config")) {
     if (value < 0 || value >= N_MV_CFG) return fail("mfe_set_option: matvec_config must be in [0,%d)", (int)N_MV_CFG);
-    CK(cudaSetDevice(c->device));
     c->mv_cfg = (int)value;
-    if (c->tr != matvec_configs[value].tr) {
-      c->tr = matvec_configs[value].tr;
-      if (c->has_structure) { CK(cudaStreamSynchronize(c->stream)); if (build_tile_base(c)) return 1; CK(cudaStreamSynchronize(c->stream)); }
-    }
     return 0;
   }
-  if (!strcmp(name, "matvec_flags")) { c->mv_flags = (int)value; return 0; }
-  if (!strcmp(name, "matvec_line_tiles")) { c->mv_line_tiles = (int)value; return 0; }
-  if (!strcmp(name, "dot_maps_version")) { if (value != 1 && value != 2) return fail("dot_maps_version must be 1 or 2"); c->dot_maps_ver = (int)value; return 0; }
+  if (!strcmp(name, "dot_maps_warps")) {
+    if (value != 0 && value != 16 && value != 24) return fail("mfe_set_option: dot_maps_warps must be 0, 16 or 24");
+    c->dot_maps_warps = (int)value;
+    return 0;
+  }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
 
@@ -1028,12 +1021,12 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
   CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   auto body = [&](int rep) -> int {
-    if (!strcmp(what, "matvec")) return launch_matvec_local(c, c->d_p, c->d_Ap, nullptr, nullptr, 0);
-    if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, c->d_p, c->d_Ap, c->d_tile_sums, nullptr, 0);
+    if (!strcmp(what, "matvec")) return launch_matvec_local(c, c->d_p, c->d_Ap, false, nullptr, 0);
+    if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, c->d_p, c->d_Ap, true, nullptr, 0);
     if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n); c->launches++; return 0; }
     if (!strcmp(what, "stream_probe")) {
       constexpr int PG = 16, PS = 1;
-      const size_t smem = (size_t)PG * PS * MatvecCfg<32>::SLOT_BYTES + (size_t)PG * PS * 8 + 64;
+      const size_t smem = (size_t)PG * PS * MatvecCfg::SLOT_BYTES + (size_t)PG * PS * 8 + 64;
       auto kern = k_stream_probe<PG, PS>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return fail("stream_probe: smem attribute");
       if (c->tr != 32) return fail("stream_probe needs a 32-row tile configuration");
@@ -1042,7 +1035,7 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
     }
     if (!strcmp(what, "stream_probe21")) {
       constexpr int PG = 21, PS = 1;
-      const size_t smem = (size_t)PG * PS * MatvecCfg<32>::SLOT_BYTES + (size_t)PG * PS * 8 + 64;
+      const size_t smem = (size_t)PG * PS * MatvecCfg::SLOT_BYTES + (size_t)PG * PS * 8 + 64;
       auto kern = k_stream_probe<PG, PS>;
       if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return fail("stream_probe: smem attribute");
       if (c->tr != 32) return fail("stream_probe needs a 32-row tile configuration");
@@ -1052,7 +1045,7 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
     if (!strcmp(what, "waxpby")) { launch_waxpby(c, n, one, c->d_r, half, c->d_p, c->d_tmp1, nullptr, 0); return 0; }
     if (!strcmp(what, "dot_rr")) return launch_dot(c, n, c->d_r, c->d_r, 0, EPI_NONE, 0, false, nullptr);
     if (!strcmp(what, "dot_pap")) return launch_dot(c, n, c->d_Ap, c->d_p, 0, EPI_NONE, 0, false, nullptr);
-    if (!strcmp(what, "xr_update")) { k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.w.chunk_sums, nullptr, 0); c->launches++; return 0; }
+    if (!strcmp(what, "xr_update")) { k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.piece_sums_a, c->dot.chunk_sums_a, nullptr, nullptr, nullptr, 0); c->launches++; return 0; }
     (void)rep;
     return fail("mfe_time_kernel: unknown kernel '%s'", what);
   };

@@ -1,0 +1,528 @@
+// dot_kernels.cuh -- device side of the order-reproducing dot product (exact_dot.h) and of the fused CG vector
+// updates that feed it.  ref/src/Vector_functions.hpp:194-226 (dot), ref/src/cg_solve.hpp:157-212.
+//
+// Pipeline of one exact dot over n terms (piece = 512 terms = one warp, chunk = 8 pieces):
+//   producer   plain sums of the products per piece and per chunk -- written by the kernel that produced the
+//              operands (k_xr_update for r.r, the SpMV for p.Ap) or by k_chunk_sums; they only PREDICT binades
+//   k_dot_maps persistent TMA-staged pass over the operands: one DotMap per leaf, collapsed per piece, chunk,
+//              super and hyper (arrival tickets); leaves where the predicted binade changes are listed as dirty
+//   k_dot_walk one CTA: clean gaps between dirty leaves collapse to one map each (one warp per gap), thread 0
+//              applies  [gap][dirty leaf][gap] ...  in order and runs the CG scalar epilogue
+#pragma once
+#include "kernels.cuh"
+
+namespace mfe {
+
+// ------------------------------------------------------------------------------------------------------
+// producers of the prediction sums
+// ------------------------------------------------------------------------------------------------------
+// cg_solve.hpp:211-212 fused:  x = 1*x + alpha*p ;  r = 1*r + (-alpha)*Ap ;  plain sums of r*r per piece / chunk
+// (binade prediction for the next exact dot).  One CTA per chunk, one warp per piece (a warp instruction touches
+// 256 contiguous bytes per operand).  Also zeroes the p.Ap prediction sums that the next SpMV accumulates into.
+__global__ void __launch_bounds__(DOT_CTA_THREADS) k_xr_update(int64_t n, const CgScalars *sc, const double *__restrict__ p,
+                                                               const double *__restrict__ Ap, double *__restrict__ x,
+                                                               double *__restrict__ r, double *__restrict__ piece_sums,
+                                                               double *__restrict__ chunk_sums, double *__restrict__ zero_piece_sums,
+                                                               double *__restrict__ zero_chunk_sums, const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  __shared__ double sh[DOT_PIECES_PER_CHUNK];
+  const double alpha = sc->alpha, nalpha = sc->neg_alpha, one = 1.0;
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t piece = (int64_t)blockIdx.x * DOT_PIECES_PER_CHUNK + wq;
+  const int64_t base = piece * DOT_PIECE;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int it = 0; it < DOT_LEAF; ++it) {
+    const int64_t i = base + it * 32 + lane;
+    if (i < n) {
+      x[i] = __dadd_rn(__dmul_rn(one, x[i]), __dmul_rn(alpha, p[i]));
+      const double rn = __dadd_rn(__dmul_rn(one, r[i]), __dmul_rn(nalpha, Ap[i]));
+      r[i] = rn;
+      acc += rn * rn;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    sh[wq] = acc;
+    if (base < n) { piece_sums[piece] = acc; if (zero_piece_sums) zero_piece_sums[piece] = 0.0; }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < DOT_PIECES_PER_CHUNK; ++q) t += sh[q];
+    chunk_sums[blockIdx.x] = t;
+    if (zero_chunk_sums) zero_chunk_sums[blockIdx.x] = 0.0;
+  }
+}
+
+// plain per-piece / per-chunk sums of x*y (when no producer kernel supplied them)
+__global__ void __launch_bounds__(DOT_CTA_THREADS) k_chunk_sums(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                                                double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
+                                                                const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  __shared__ double sh[DOT_PIECES_PER_CHUNK];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int64_t piece = (int64_t)blockIdx.x * DOT_PIECES_PER_CHUNK + wq;
+  const int64_t base = piece * DOT_PIECE;
+  double acc = 0.0;
+#pragma unroll 8
+  for (int it = 0; it < DOT_LEAF; ++it) {
+    const int64_t i = base + it * 32 + lane;
+    if (i < n) acc += x[i] * y[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) { sh[wq] = acc; if (base < n) piece_sums[piece] = acc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < DOT_PIECES_PER_CHUNK; ++q) t += sh[q];
+    chunk_sums[blockIdx.x] = t;
+  }
+}
+
+// Exclusive prefix over chunk sums; chunk_prefix[nchunks] = total (the MFE_DOT_TREE result).  One CTA.
+__global__ void __launch_bounds__(1024) k_chunk_prefix(const double *__restrict__ sums, int nchunks, double *__restrict__ chunk_prefix,
+                                                       const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  __shared__ double wtot[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // block scan: each thread owns a contiguous run of chunks
+  const int runlen = (nchunks + blockDim.x - 1) / blockDim.x;
+  const int c0 = threadIdx.x * runlen, c1 = min(nchunks, c0 + runlen);
+  double run = 0.0;
+  for (int c = c0; c < c1; ++c) run += sums[c];
+  double inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    double v = lane < nw ? wtot[lane] : 0.0, iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+    wtot[lane] = iv - v;                           // exclusive warp offsets
+  }
+  __syncthreads();
+  double pre = wtot[warp] + (inc - run);
+  for (int c = c0; c < c1; ++c) { const double v = sums[c]; chunk_prefix[c] = pre; pre += v; }
+  if (c1 == nchunks && c0 < nchunks) chunk_prefix[nchunks] = pre;
+  if (nchunks == 0 && threadIdx.x == 0) chunk_prefix[0] = 0.0;
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_f64_off(uint32_t addr)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// ordered map compositions inside a warp
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ DotMap shfl_up_map(const DotMap &m, int o)
+{
+  DotMap r;
+  r.a0 = __shfl_up_sync(0xffffffffu, m.a0, o); r.a1 = __shfl_up_sync(0xffffffffu, m.a1, o);
+  r.lo = __shfl_up_sync(0xffffffffu, m.lo, o); r.hi = __shfl_up_sync(0xffffffffu, m.hi, o);
+  r.hyp = __shfl_up_sync(0xffffffffu, m.hyp, o); r.pad = 0;
+  return r;
+}
+// ordered warp reduction: lane 31 ends with the composition of lanes 32-WIDTH..31 in lane order
+template <int WIDTH = 32>
+__device__ __forceinline__ DotMap warp_compose(DotMap m, int lane)
+{
+#pragma unroll
+  for (int o = 1; o < WIDTH; o <<= 1) {
+    const DotMap u = shfl_up_map(m, o);
+    if (lane >= o) m = dot_compose(u, m);
+  }
+  return m;
+}
+__device__ __forceinline__ DotMap load_map_cg(const DotMap *src)
+{
+  DotMap m;
+  m.a0 = __ldcg(&src->a0); m.a1 = __ldcg(&src->a1); m.lo = __ldcg(&src->lo); m.hi = __ldcg(&src->hi); m.hyp = __ldcg(&src->hyp); m.pad = __ldcg(&src->pad);
+  return m;
+}
+
+// level 2 -> 3 -> 4 of the map hierarchy, called by a whole warp with the map of chunk c on lane 31: the last chunk
+// of a group of 32 to arrive collapses the group (arrival tickets reset themselves, so the workspace is reusable
+// without a memset).
+__device__ __forceinline__ void dot_publish_chunk_map(const DotWork &w, const DotMap &cmap, int lane, int c, int nchunks)
+{
+  const int sgrp = c >> 5, ssize = min(32, nchunks - (sgrp << 5));
+  int last = 0;
+  if (lane == 31) {
+    w.cta_maps[c] = cmap;
+    __threadfence();
+    last = atomicAdd(&w.super_cnt[sgrp], 1) == ssize - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 31);
+  if (!last) return;
+  __threadfence();
+  DotMap sm = dot_identity();
+  if (lane < ssize) { sm = load_map_cg(w.cta_maps + ((int64_t)sgrp << 5) + lane); sm.pad = 0; }
+  sm = warp_compose(sm, lane);
+  const int nsupers = (nchunks + 31) >> 5;
+  const int hgrp = sgrp >> 5, hsize = min(32, nsupers - (hgrp << 5));
+  if (lane == 31) {
+    w.super_maps[sgrp] = sm;
+    w.super_cnt[sgrp] = 0;
+    __threadfence();
+    last = atomicAdd(&w.hyper_cnt[hgrp], 1) == hsize - 1;
+  }
+  last = __shfl_sync(0xffffffffu, last, 31);
+  if (!last) return;
+  __threadfence();
+  DotMap hm = dot_identity();
+  if (lane < hsize) { hm = load_map_cg(w.super_maps + ((int64_t)hgrp << 5) + lane); hm.pad = 0; }
+  hm = warp_compose(hm, lane);
+  if (lane == 31) { w.hyper_maps[hgrp] = hm; w.hyper_cnt[hgrp] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Exact dot, map phase.  Persistent CTAs of NW independent warps; CTA b owns the contiguous pieces
+// [b*PP, (b+1)*PP).  Every warp arms its own shared-memory stage with 1-D bulk async copies (TMA engine) of the
+// 4 KB per operand of its next piece, waits on its mbarrier, and turns the piece into one DotMap:
+//   * lane l owns leaf l (terms 16 l .. 16 l + 15) and reads it in the rotated order i ^ (l & 15): bank-conflict
+//     free, and legal because the common "simple" leaf formulation is order independent (exact_dot.h);
+//   * the predicted running sum at the piece start comes from a per-CTA table (prefix of the producer's piece
+//     sums), the prediction inside the piece from a warp scan of the leaf sums;
+//   * simple leaves compose in floating point (a, lo, hi as exact integers in doubles); a piece with any other
+//     leaf takes the general int64 composition;
+//   * the last piece of a chunk to arrive (ticket) collapses the chunk and feeds the super / hyper tickets.
+// The bytes in flight are the stages of the waiting warps, as in k_matvec.
+// ------------------------------------------------------------------------------------------------------
+enum { DOT_MAPS_MAX_PP = 2048 };     // pieces per CTA (bounds the prefix table in shared memory)
+
+template <bool SAME, int NW>
+struct DotMapsCfg {
+  static constexpr int STAGE_BYTES = (SAME ? 1 : 2) * DOT_PIECE * 8;
+  static constexpr int MAX_CHUNKS = DOT_MAPS_MAX_PP / DOT_PIECES_PER_CHUNK + 2;      // chunks a CTA's range can touch
+  static constexpr size_t SMEM_BYTES = (size_t)NW * STAGE_BYTES + (size_t)NW * 8 /*mbarriers*/ + (size_t)(DOT_MAPS_MAX_PP + 1) * 8 /*table*/ +
+                                       (size_t)2 * NW * 8 /*reductions*/ + (size_t)MAX_CHUNKS * 4 /*arrival counters*/ + 64;
+};
+
+template <bool SAME, int NW>
+__global__ void __launch_bounds__(32 * NW, 1)
+k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y, DotWork w, int npieces, int PP, const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  constexpr int STAGE = DotMapsCfg<SAME, NW>::STAGE_BYTES;
+  constexpr int NT = 32 * NW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
+  double *stage = reinterpret_cast<double *>(smem + (size_t)wq * STAGE);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)NW * STAGE) + wq;
+  double *table = reinterpret_cast<double *>(smem + (size_t)NW * STAGE + (size_t)NW * 8);
+  double *red = table + (DOT_MAPS_MAX_PP + 1);                  // [2][NW]
+  int *ccnt = reinterpret_cast<int *>(red + 2 * NW);            // arrivals per chunk of this CTA's range
+  const int nchunks = (npieces + DOT_PIECES_PER_CHUNK - 1) / DOT_PIECES_PER_CHUNK;
+  const int p0 = blockIdx.x * PP;
+  const int np = min(PP, npieces - p0);                         // pieces of this CTA
+  if (np <= 0) return;
+
+  auto issue = [&](int piece) {
+    const int64_t b = (int64_t)piece * DOT_PIECE;
+    const int64_t cntp = n - b < DOT_PIECE ? n - b : DOT_PIECE;
+    const uint32_t bytes = (uint32_t)(((cntp + 1) & ~1LL) * 8);  // multiple of 16; the vectors carry >= 8 doubles of slack
+    mbar_expect_tx(bar, SAME ? bytes : 2 * bytes);
+    bulk_g2s(stage, x + b, bytes, bar);
+    if (!SAME) bulk_g2s(stage + DOT_PIECE, y + b, bytes, bar);
+  };
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < DotMapsCfg<SAME, NW>::MAX_CHUNKS; i += NT) ccnt[i] = 0;
+  __syncthreads();
+  if (lane == 0 && wq < np) issue(p0 + wq);                     // first piece of every warp is in flight during the prologue
+
+  // ---- prologue: predicted running sum at the start of every piece of this CTA ----
+  {
+    const int c0 = p0 / DOT_PIECES_PER_CHUNK;
+    double part = 0.0;
+    for (int i = tid; i < c0; i += NT) part += w.chunk_sums[i];
+    if (tid < p0 - c0 * DOT_PIECES_PER_CHUNK) part += w.piece_sums[c0 * DOT_PIECES_PER_CHUNK + tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    // runs of R consecutive pieces per thread
+    const int R = (np + NT - 1) / NT, j0 = tid * R;
+    double run = 0.0;
+    for (int q = 0; q < R; ++q) if (j0 + q < np) run += w.piece_sums[p0 + j0 + q];
+    double inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) red[NW + wq] = inc;
+    if (lane == 0) red[wq] = part;
+    __syncthreads();
+    double B0 = 0.0, woff = 0.0;
+#pragma unroll
+    for (int q = 0; q < NW; ++q) { B0 += red[q]; if (q < wq) woff += red[NW + q]; }
+    double acc = woff + (inc - run);
+    for (int q = 0; q < R; ++q) if (j0 + q < np) { table[j0 + q] = B0 + acc; acc += w.piece_sums[p0 + j0 + q]; }
+    if (tid == NT - 1) table[np] = B0 + acc;
+    __syncthreads();
+  }
+
+  uint32_t parity = 0;
+  for (int j = wq; j < np; j += NW) {
+    const int piece = p0 + j;
+    const int64_t lbeg = (int64_t)piece * DOT_PIECE + lane * DOT_LEAF;
+    const int cnt = (int)(lbeg >= n ? 0 : (n - lbeg < DOT_LEAF ? n - lbeg : DOT_LEAF));
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    const double *xs = stage + lane * DOT_LEAF, *ys = SAME ? xs : xs + DOT_PIECE;
+    // products rounded once (fl(x*y)) exactly as the serial loop forms them
+    double prod[DOT_LEAF];
+    if (cnt == DOT_LEAF) {
+      // byte address of element i ^ rot of this lane's leaf: the leaf base is 128-byte aligned, so OR = ADD
+      const uint32_t lbase = smem_u32(xs), rotb = (uint32_t)(lane & (DOT_LEAF - 1)) * 8u;
+#pragma unroll
+      for (int i = 0; i < DOT_LEAF; ++i) {
+        const uint32_t a = lbase | ((uint32_t)(i * 8) ^ rotb);
+        const double xv = lds_f64(a);
+        prod[i] = SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(a));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < DOT_LEAF; ++i) prod[i] = i < cnt ? __dmul_rn(xs[i], ys[i]) : 0.0;
+    }
+    double ls = 0.0;
+#pragma unroll
+    for (int i = 0; i < DOT_LEAF; ++i) ls += prod[i];
+    double inc = ls;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    const double pre = table[j] + (inc - ls);
+    const int hyp = dot_hyp_of(pre);
+    int hyp_end = __shfl_down_sync(0xffffffffu, hyp, 1);       // predicted binade at the start of the next leaf
+    if (lane == 31) hyp_end = dot_hyp_of(table[j + 1]);
+
+    bool simple = false, risky = false;
+    double sa = 0.0, slo = 0.0, shi = 0.0;
+    DotMap m = dot_identity();
+    if (cnt == DOT_LEAF && hyp >= 0 && hyp != HYP_ZERO) {
+      simple = dot_leaf16_simple(prod, hyp, pre, sa, slo, shi);
+      if (!simple) {                                           // exact tie / near a binade boundary: ordered, exact bounds
+#pragma unroll
+        for (int i = 0; i < DOT_LEAF; ++i) prod[i] = SAME ? __dmul_rn(xs[i], xs[i]) : __dmul_rn(xs[i], ys[i]);
+        m = dot_leaf_map16_fp(prod, hyp);
+        risky = dot_leaf_risky(m, hyp, pre);
+      }
+    } else if (cnt == DOT_LEAF) {
+      m = dot_leaf_map16(prod, hyp, pre);                      // hyp < 0, or the running sum is exactly +0.0 (order independent)
+    } else if (cnt > 0) {
+      m = dot_leaf_map(x, y, lbeg, lbeg + cnt, hyp);           // ragged last leaf of the vector
+    }
+    const bool dirty = cnt > 0 && ((!simple && m.hyp == HYP_INVALID) || hyp != hyp_end || risky);
+    const bool piece_dirty = __any_sync(0xffffffffu, dirty);
+    __syncwarp();
+    if (lane == 0 && j + NW < np) issue(piece + NW);           // the stage is free: next piece in flight while we publish
+
+    // ordered collapse of the 32 leaves onto lane 31
+    const int hyp0 = __shfl_sync(0xffffffffu, hyp, 0);
+    const bool all_simple = __all_sync(0xffffffffu, simple && hyp == hyp0);
+    DotMap wm;
+    if (all_simple) {
+      // simple maps compose in floating point: a = fa + ga, lo = min(flo, fa + glo), hi = max(fhi, fa + ghi); every
+      // value is an exact integer while below 2^53, and a map that ever exceeds 2^52 is unusable (checked below)
+      double ca = sa, clo = slo, chi = shi;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double fa = __shfl_up_sync(0xffffffffu, ca, o), flo = __shfl_up_sync(0xffffffffu, clo, o), fhi = __shfl_up_sync(0xffffffffu, chi, o);
+        if (lane >= o) {
+          const double nlo = fa + clo, nhi = fa + chi;
+          clo = flo < nlo ? flo : nlo;
+          chi = fhi > nhi ? fhi : nhi;
+          ca = fa + ca;
+        }
+      }
+      if (clo > -4503599627370496.0 && chi < 4503599627370496.0) {
+        wm.a0 = (long long)ca; wm.a1 = wm.a0; wm.lo = (long long)clo; wm.hi = (long long)chi; wm.hyp = hyp0; wm.pad = 0;
+      } else wm = dot_invalid();
+    } else {
+      if (simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
+      wm = warp_compose(m, lane);
+    }
+    if (piece_dirty) {
+      // keep the 32 leaf maps so that the walker can stitch around the dirty leaves of this piece
+      if (all_simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
+      w.leaf_maps[(int64_t)piece * 32 + lane] = m;
+      if (dirty) {
+        const int slot = atomicAdd(w.dirty_count, 1);
+        if (slot < DOT_MAX_DIRTY) w.dirty_list[slot] = piece * 32 + lane;
+      }
+    }
+    // publish the piece map.  The pieces of a chunk belong to this CTA (except at the two ends of its range), so
+    // arrivals are counted in shared memory with a CTA-scope fence; only the warp that completes a chunk pays the
+    // device-scope fence + ticket of the chunk level.
+    const int c = piece / DOT_PIECES_PER_CHUNK;
+    const int cfirst = c * DOT_PIECES_PER_CHUNK;
+    const int nin = min(DOT_PIECES_PER_CHUNK, npieces - cfirst);                         // pieces the chunk has
+    const int mine = min(p0 + np, cfirst + nin) - max(p0, cfirst);                       // ... of which in this CTA's range
+    int last = 0;
+    if (lane == 31) {
+      wm.pad = piece_dirty ? 1 : 0;
+      w.warp_maps[piece] = wm;
+      __threadfence_block();
+      last = atomicAdd(&ccnt[c - p0 / DOT_PIECES_PER_CHUNK], 1) == mine - 1;
+      if (last && mine != nin) {                     // chunk shared with a neighbouring CTA: device-wide ticket
+        __threadfence();
+        last = atomicAdd(&w.chunk_cnt[c], mine) + mine == nin;
+        if (last) w.chunk_cnt[c] = 0;
+      }
+    }
+    last = __shfl_sync(0xffffffffu, last, 31);
+    if (last) {
+      __threadfence();
+      // the (up to) 8 piece maps sit on lanes 24..31; three ordered steps leave their composition on lane 31
+      DotMap cm = dot_identity();
+      const int q = lane - (32 - DOT_PIECES_PER_CHUNK);
+      if (q >= 0 && q < nin) { cm = load_map_cg(w.warp_maps + cfirst + q); cm.pad = 0; }
+      cm = warp_compose<DOT_PIECES_PER_CHUNK>(cm, lane);
+      if (lane == 31) cm.pad = 1;
+      dot_publish_chunk_map(w, cm, lane, c, nchunks);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Exact dot, walk phase: one CTA.  (1) sort the dirty leaves, fetch their products; (2) one warp per gap: the
+// <= 9 runs of the gap are loaded at once (one map per lane and run) and collapsed by ordered shuffle scans into
+// ONE map per gap; (3) thread 0 walks  [gap 0][dirty leaf 0][gap 1][dirty leaf 1] ... [gap D]  -- ~2 short steps
+// per dirty leaf.  Any map that fails its check is replayed from global memory in plain floating point, so the
+// result is the serial loop's for every input.
+// ------------------------------------------------------------------------------------------------------
+enum { WALK_THREADS = 512 };
+
+__global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                                          DotWork w, CgScalars *sc, int epi, int k,
+                                                          double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
+                                                          const CgScalars *gate)
+{
+  if (cg_gate_closed(gate, k)) return;
+  __shared__ int dirty[DOT_MAX_DIRTY];
+  __shared__ int sorted[DOT_MAX_DIRTY];
+  __shared__ DotMap gmaps[DOT_MAX_DIRTY + 1];
+  __shared__ double replay_prod[DOT_MAX_DIRTY * DOT_LEAF];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = *w.dirty_count;
+  const long long nleaves = ((n + DOT_PIECE - 1) / DOT_PIECE) * 32;     // whole pieces: the maps that exist
+  double s = 0.0;
+  if (D > DOT_MAX_DIRTY) {                     // pathological input: the literal loop
+    if (tid == 0) s = dot_replay(x, y, 0, n, 0.0);
+  } else {
+    for (int i = tid; i < D; i += WALK_THREADS) dirty[i] = w.dirty_list[i];
+    __syncthreads();
+    for (int i = tid; i < D; i += WALK_THREADS) {        // rank sort (leaf indices are distinct)
+      const int v = dirty[i]; int rk = 0;
+      for (int j = 0; j < D; ++j) rk += dirty[j] < v;
+      sorted[rk] = v;
+    }
+    __syncthreads();
+    // products of the dirty leaves, fetched by all threads at once (the sequential walk then reads smem only)
+    for (int q = tid; q < D * DOT_LEAF; q += WALK_THREADS) {
+      const int64_t i = (int64_t)sorted[q / DOT_LEAF] * DOT_LEAF + (q % DOT_LEAF);
+      replay_prod[q] = i < n ? __dmul_rn(x[i], y[i]) : 0.0;
+    }
+    for (int g = warp; g <= D; g += WALK_THREADS / 32) {
+      const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
+      WalkPiece pc[DOT_GAP_PIECES];
+      dot_gap_decompose(lo, hi, pc);
+      // the maps of the gap in application order form one flat list; lane l takes a contiguous slice of it
+      int total = 0;
+#pragma unroll
+      for (int q = 0; q < DOT_GAP_PIECES; ++q) total += pc[q].count;
+      const int per = (total + 31) / 32, f0 = lane * per, f1 = min(total, f0 + per);
+      DotMap gm = dot_identity();
+      for (int base = f0; base < f1; base += 8) {
+        DotMap buf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int f = base + u;
+          if (f < f1) {
+            int q = 0;
+#pragma unroll
+            for (int t = 0; t < DOT_GAP_PIECES - 1; ++t) if (q == t && f >= pc[t].count) { f -= pc[t].count; q = t + 1; }
+            buf[u] = load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (base + u < f1) gm = dot_compose(gm, buf[u]);
+      }
+      gm = warp_compose(gm, lane);
+      if (lane == 31) gmaps[g] = gm;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int g = 0; g <= D; ++g) {
+        const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
+        if (lo < hi && !dot_apply(gmaps[g], s)) s = dot_walk_gap_slow(lo, hi, w, x, y, n, s);
+        if (g < D) {
+          const int64_t b = (int64_t)sorted[g] * DOT_LEAF;
+          const int cnt = (int)(b + DOT_LEAF <= n ? DOT_LEAF : n - b);
+          double pr[DOT_LEAF];
+#pragma unroll
+          for (int i = 0; i < DOT_LEAF; ++i) pr[i] = replay_prod[g * DOT_LEAF + i];
+#pragma unroll
+          for (int i = 0; i < DOT_LEAF; ++i) if (i < cnt) s = __dadd_rn(s, pr[i]);
+        }
+      }
+    }
+  }
+  if (tid == 0) {
+    *w.result = s;
+    *w.dirty_count = 0;                         // ready for the next dot on this workspace
+    if (sc) {
+      sc->dot_local = s;
+      if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist);
+    }
+  }
+}
+
+// the literal serial loop on one device thread (MFE_DOT_SERIAL; validation of the exact dot)
+__global__ void k_dot_serial(int64_t n, const double *__restrict__ x, const double *__restrict__ y, double *result, CgScalars *sc,
+                             int epi, int k, double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
+                             const CgScalars *gate)
+{
+  if (cg_gate_closed(gate, k)) return;
+  const double s = dot_replay(x, y, 0, n, 0.0);
+  *result = s;
+  if (sc) { sc->dot_local = s; if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist); }
+}
+// MFE_DOT_TREE: the total left by k_chunk_prefix
+__global__ void k_dot_tree_finish(const double *chunk_prefix, int nchunks, double *result, CgScalars *sc, int epi, int k,
+                                  double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist, const CgScalars *gate)
+{
+  if (cg_gate_closed(gate, k)) return;
+  const double s = chunk_prefix[nchunks];
+  *result = s;
+  if (sc) { sc->dot_local = s; if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist); }
+}
+// multi-rank: rank-ordered sum of the gathered local dots ((r0+r1)+r2)+..., then the scalar bookkeeping
+__global__ void k_dot_allreduce_finish(const double *gathered, int nranks, double *result, CgScalars *sc, int epi, int k,
+                                       double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist, const CgScalars *gate)
+{
+  if (cg_gate_closed(gate, k)) return;
+  double g = gathered[0];
+  for (int p = 1; p < nranks; ++p) g = __dadd_rn(g, gathered[p]);
+  *result = g;
+  if (sc && epi != EPI_NONE) cg_epilogue(sc, epi, k, g, normr_hist, rtrans_hist, pap_hist, alpha_hist);
+}
+
+}  // namespace mfe

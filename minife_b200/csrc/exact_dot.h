@@ -41,8 +41,10 @@ static inline double mfe_u2d_(uint64_t u) { double x; memcpy(&x, &u, 8); return 
 namespace mfe {
 
 enum { DOT_LEAF = 16 };                 // terms per leaf (one thread)
-enum { DOT_CTA_THREADS = 256 };         // leaves per chunk
-enum { DOT_CHUNK = DOT_LEAF * DOT_CTA_THREADS };   // 4096 terms per chunk (one CTA)
+enum { DOT_CTA_THREADS = 256 };         // leaves per chunk (and threads of the per-chunk producer kernels)
+enum { DOT_CHUNK = DOT_LEAF * DOT_CTA_THREADS };   // 4096 terms per chunk
+enum { DOT_PIECE = DOT_LEAF * 32 };                // 512 terms per piece (one warp: 32 leaves)
+enum { DOT_PIECES_PER_CHUNK = DOT_CHUNK / DOT_PIECE };
 enum { DOT_MAX_DIRTY = 256 };           // more dirty leaves than this -> whole-vector serial replay
 
 enum { HYP_INVALID = -1,   // map unusable: replay
@@ -332,6 +334,21 @@ MFE_HD bool dot_leaf16_simple(const double *prod, int hyp, double pre, double &a
   return true;
 }
 
+// A leaf whose exact bounds, applied to the PREDICTED significand of the running sum, come within
+// MFE_DOT_RISK_MARGIN ulps of either end of the binade will probably fail dot_apply (the running sum dips across
+// the boundary inside the leaf even though it starts and ends in the same binade -- mixed-sign data).  Such
+// leaves are listed as dirty, so that the walker replays them instead of discovering the failure in a collapsed
+// gap (whose recovery is slow).  Prediction only: a miss costs time, never correctness.
+#define MFE_DOT_RISK_MARGIN 1048576.0   /* 2^20 ulps */
+MFE_HD bool dot_leaf_risky(const DotMap &m, int hyp, double pre)
+{
+  if (m.hyp < 0 || m.hyp == HYP_ZERO) return false;
+  const int k = 1075 - (hyp & 0x7ff);
+  const int k1 = k / 2, k2 = k - k1;
+  const double Sp = fabs(MFE_DMUL(MFE_DMUL(pre, dot_pow2(k1)), dot_pow2(k2)));     // |pre| / ulp, in [2^52, 2^53)
+  return !((Sp + (double)m.lo) - MFE_DOT_RISK_MARGIN > 4503599627370496.0 && (Sp + (double)m.hi) + MFE_DOT_RISK_MARGIN < 9007199254740992.0);
+}
+
 MFE_HD DotMap dot_leaf_map16(const double *prod, int hyp, double pre)
 {
   if (hyp < 0) return dot_invalid();
@@ -392,9 +409,9 @@ MFE_HD double dot_replay(const double *x, const double *y, long long begin, long
 
 // ---------------------------------------------------------------------------------------------------------
 // Map hierarchy + the sequential part of the walk (shared by the kernels and the CPU test harness).
-//   level 0  leaf   DOT_LEAF terms            leaf_maps   (stored for dirty chunks only)
-//   level 1  warp   32 leaves                 warp_maps   (stored for dirty chunks only)
-//   level 2  chunk  8 warps  = 256 leaves     cta_maps
+//   level 0  leaf   DOT_LEAF terms            leaf_maps   (stored only for pieces that hold a dirty leaf)
+//   level 1  piece  32 leaves (one warp)      warp_maps   (always stored; pad = 1 when its leaf maps are stored)
+//   level 2  chunk  8 pieces = 256 leaves     cta_maps
 //   level 3  super  32 chunks = 8192 leaves   super_maps
 //   level 4  hyper  32 supers = 262144 leaves hyper_maps
 // A clean stretch of leaves [lo,hi) between two dirty leaves decomposes, segment-tree style, into <= 9 runs of
@@ -408,15 +425,17 @@ MFE_HD int dot_level_size(int level)   // in leaves
 }
 
 struct DotWork {
-  double *chunk_sums;      // nchunks plain partial sums (binade prediction)
-  double *chunk_prefix;    // nchunks + 1 exclusive prefix of the above
-  DotMap *leaf_maps;       // level 0: nchunks * 256
-  DotMap *warp_maps;       // level 1: nchunks * 8
-  DotMap *cta_maps;        // level 2: nchunks       (pad = 1 marks a dirty chunk: its level 0/1 maps are stored)
+  double *chunk_sums;      // nchunks plain partial sums of the products (binade prediction; written by the producer kernel)
+  double *piece_sums;      // npieces = 8 per chunk, same purpose
+  double *chunk_prefix;    // nchunks + 1 exclusive prefix of chunk_sums (MFE_DOT_TREE only)
+  DotMap *leaf_maps;       // level 0: nchunks * 256 (stored only for pieces that hold a dirty leaf)
+  DotMap *warp_maps;       // level 1: npieces       (pad = 1: the 32 leaf maps of this piece are stored)
+  DotMap *cta_maps;        // level 2: nchunks       (pad = 1: the level-1 maps below are stored -- always)
   DotMap *super_maps;      // level 3: ceil(nchunks / 32)
   DotMap *hyper_maps;      // level 4: ceil(nsupers / 32)
-  int *super_cnt;          // arrival tickets (self-resetting)
-  int *hyper_cnt;
+  int *chunk_cnt;          // arrival tickets (self-resetting): pieces of a chunk
+  int *super_cnt;          //                                    chunks of a super
+  int *hyper_cnt;          //                                    supers of a hyper
   int *dirty_count;        // 1
   int *dirty_list;         // DOT_MAX_DIRTY leaf indices
   double *result;          // 1
@@ -477,7 +496,7 @@ MFE_HD double dot_apply_or_descend(const DotWork &w, int level, long long index,
     if (b >= n) continue;
     const DotMap m = dot_level_maps(w, L)[I];
     if (dot_apply(m, s)) continue;
-    bool children_stored = L >= 3 || (L == 2 && m.pad == 1) || L == 1;
+    const bool children_stored = L >= 3 || ((L == 2 || L == 1) && m.pad == 1);
     if (L == 0 || !children_stored) {
       long long e = b + (long long)dot_level_size(L) * DOT_LEAF; if (e > n) e = n;
       s = dot_replay(x, y, b, e, s);

@@ -1,0 +1,269 @@
+// spmv.cuh -- CSR SpMV  y = A x  for sm_100a: ref/src/SparseMatrix_functions.hpp:546-578 (matvec_std, local part).
+//
+// CSR-stream design: the nnz range of 32 consecutive rows (a tile) is contiguous in packed_coefs / packed_cols, so
+// it is staged into shared memory by two 1-D bulk async copies (TMA engine, SASS UBLKCP; full 128-byte HBM bursts
+// whatever the row lengths; the matrix stream is marked L2 evict_first so that x stays cached), then lane r walks
+// ITS row in storage order: sum = fl(sum + fl(coef*x[col])) -- the reference's exact sequence, no FMA.  x is
+// gathered through L1/L2 (consecutive rows read consecutive x -> coalesced).
+//
+// One WARP per tile, G warps per CTA, S smem stages per warp, one persistent CTA per SM.  With S = 1 a warp arms
+// its stage, waits, consumes, re-arms: the bytes in flight are the stages of the warps that are waiting, and
+// 16 warps x 10.5 KB saturate HBM (measured 7.0 TB/s algorithmic at 256^3 = 98 % of the bare TMA stream,
+// k_stream_probe).  The consumer is specialised: when every row of the tile holds exactly 27 entries (interior of
+// the hex8 mesh, ~87 % of the tiles at 256^3) the row walk has no predication at all -- per entry LDS.64 coef,
+// LDS col, IMAD.WIDE, LDG x, DMUL, DADD -- and any other staged tile uses predicated adds (the select stays off
+// the dependent chain).  H gather batches per row trade one extra gather latency for fewer registers.
+//
+// Optionally accumulates plain sums of x[row]*y[row] per 512-row piece and per 4096-row chunk (binade prediction
+// for the exact dot, exact_dot.h -- those values steer speed only, never results).
+#pragma once
+#include "kernels.cuh"
+
+namespace mfe {
+
+enum { MV_TILE_ROWS = 32 };
+struct MatvecCfg {
+  static constexpr int CAP = MV_TILE_ROWS * 27 + 8;                // nnz capacity of one stage
+  static constexpr int SLOT_BYTES = ((CAP * 12 + 127) / 128) * 128;
+};
+
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+               : "memory");
+}
+
+// predicated add: sum += prod when u < len.  Kept as a predicated DADD (not a select) so that the dependent
+// chain of a ragged row is one instruction per entry.
+__device__ __forceinline__ void dadd_if(double &sum, double prod, int u, int len)
+{
+  asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %2, %3;\n@p add.rn.f64 %0, %0, %1;\n}\n" : "+d"(sum) : "d"(prod), "r"(u), "r"(len));
+}
+
+template <int G, int S, int H>
+__global__ void __launch_bounds__(32 * G, 1)
+k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
+         const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
+         int64_t ntiles, int64_t nnz_padded, int zmask, double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
+         const CgScalars *gate, int k)
+{
+  if (cg_gate_closed(gate, k)) return;
+  constexpr int TR = MV_TILE_ROWS;
+  constexpr int CAP = MatvecCfg::CAP;
+  constexpr int SLOT = MatvecCfg::SLOT_BYTES;
+  constexpr int U = 27;                               // one pass covers a whole stencil row
+  constexpr int B = (U + H - 1) / H;                  // entries per gather batch
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *gbase = smem + (size_t)w * S * SLOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
+  double *racc = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + (size_t)G * S * 8);     // [8] round sums (G == 16)
+  int *rcnt = reinterpret_cast<int *>(racc + 8);                                                  // [8] round arrivals
+  uint64_t pol_stream = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  const int64_t stride = (int64_t)gridDim.x * G;      // this warp's tiles: (blockIdx.x + j * gridDim.x) * G + w
+
+  auto issue = [&](int64_t t, int s) {
+    const int64_t a0 = tile_base[t] & ~3LL;
+    int64_t a1 = (tile_base[t + 1] + 3) & ~3LL;
+    if (a1 > nnz_padded) a1 = nnz_padded;
+    const int64_t n = a1 - a0;
+    if (n <= 0 || n > CAP) return;                      // oversized tile: consumers read global memory directly
+    double *sc = reinterpret_cast<double *>(gbase + (size_t)s * SLOT);
+    int *si = reinterpret_cast<int *>(gbase + (size_t)s * SLOT + CAP * 8);
+    mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
+    bulk_g2s_hint(sc, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
+    bulk_g2s_hint(si, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 8) { racc[threadIdx.x] = 0.0; rcnt[threadIdx.x] = 0; }
+  __syncthreads();
+
+  int64_t t = (int64_t)blockIdx.x * G + w;
+  if (lane == 0)
+    for (int s = 0; s < S; ++s) { const int64_t ti = t + s * stride; if (ti < ntiles) issue(ti, s); }
+
+  uint32_t phase_bits = 0;            // expected mbarrier parity per stage (flips each time a stage completes)
+  // software-pipelined row offsets: (o0,o1) of this lane's row in the NEXT tile are loaded one tile ahead
+  uint32_t o0n = 0, o1n = 0; int64_t tb0n = 0, tb1n = 0;
+  if (t < ntiles) {
+    const int64_t r = t * TR + lane;
+    if (r < nrows) { o0n = roff[r]; o1n = roff[r + 1]; }
+    tb0n = tile_base[t]; tb1n = tile_base[t + 1];
+  }
+  for (int64_t j = 0; t < ntiles; ++j, t += stride) {
+    const int s = (int)(j % S);
+    const uint32_t parity = (phase_bits >> s) & 1u;
+    const int64_t r = t * TR + lane;
+    const uint32_t o0 = o0n, o1 = o1n;
+    const int64_t tb0 = tb0n, tb1 = tb1n;
+    const int64_t tn = t + stride;
+    if (tn < ntiles) {
+      const int64_t rn = tn * TR + lane;
+      o0n = 0; o1n = 0;
+      if (rn < nrows) { o0n = roff[rn]; o1n = roff[rn + 1]; }
+      tb0n = tile_base[tn]; tb1n = tile_base[tn + 1];
+    }
+    const int64_t a0 = tb0 & ~3LL;
+    int64_t a1 = (tb1 + 3) & ~3LL;
+    if (a1 > nnz_padded) a1 = nnz_padded;
+    const int64_t ntile = a1 - a0;
+    const bool staged = ntile > 0 && ntile <= CAP;
+    const bool live = r < nrows;
+    const int len = live ? (int)(o1 - o0) : 0;
+    const bool full = staged && __all_sync(0xffffffffu, len == U);
+
+    double sum = 0.0;                 // beta*y with beta = 0 (SparseMatrix_functions.hpp:565-568)
+    const double xr = (piece_sums && live) ? __ldg(x + r) : 0.0;
+    if (staged) {
+      mbar_wait(&bars[s], parity);
+      phase_bits ^= 1u << s;
+      const double *sc = reinterpret_cast<const double *>(gbase + (size_t)s * SLOT);
+      const int *si = reinterpret_cast<const int *>(gbase + (size_t)s * SLOT + CAP * 8);
+      // first entry of this row inside the stage: 32-bit difference to the tile's first row + tile skew
+      const int base = (int)(uint32_t)(o0 - (uint32_t)tb0) + (int)(tb0 - a0);
+      if (full) {
+        // All gathers of a batch must be in flight before its dependent add chain starts (the SM issues in order:
+        // an add placed between the loads would serialise them).  Fold a bit of every gathered value into a token
+        // that is masked to zero at run time (zmask == 0) and seed the chain with it: + 0.0, exact.
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          double cv[B], xv[B];
+#pragma unroll
+          for (int u = 0; u < B; ++u) if (h * B + u < U) { cv[u] = sc[base + h * B + u]; xv[u] = __ldg(x + si[base + h * B + u]); }
+          unsigned tok = 0;
+#pragma unroll
+          for (int u = 0; u < B; ++u) if (h * B + u < U) tok |= (unsigned)__double2hiint(xv[u]);
+          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+#pragma unroll
+          for (int u = 0; u < B; ++u) if (h * B + u < U) sum = __dadd_rn(sum, __dmul_rn(cv[u], xv[u]));
+        }
+      } else if (live) {
+        for (int i0 = 0; i0 < len; i0 += B) {
+          double cv[B], xv[B];
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const int ii = (i0 + u < len) ? base + i0 + u : base;
+            cv[u] = sc[ii];
+            xv[u] = __ldg(x + si[ii]);
+          }
+          unsigned tok = 0;
+#pragma unroll
+          for (int u = 0; u < B; ++u) tok |= (unsigned)__double2hiint(xv[u]);
+          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+#pragma unroll
+          for (int u = 0; u < B; ++u) dadd_if(sum, __dmul_rn(cv[u], xv[u]), i0 + u, len);
+        }
+      }
+    } else if (live) {
+      const int64_t b0 = tb0 + (int64_t)(uint32_t)(o0 - (uint32_t)tb0);
+      for (int64_t i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[b0 + i], __ldg(x + cols[b0 + i])));
+    }
+    double prod = 0.0;
+    if (live) { y[r] = sum; prod = xr * sum; }
+    if (piece_sums) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) prod += __shfl_down_sync(0xffffffffu, prod, o);
+    }
+    __syncwarp();                     // every lane is done with stage s -> it can be refilled
+    if (lane == 0) {
+      const int64_t t2 = t + (int64_t)S * stride;
+      if (t2 < ntiles) issue(t2, s);
+      if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
+        if (G == 16) {
+          // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
+          // rounds; the warp that completes a round publishes it).  Prediction data: a lagging warp that lets a
+          // slot be reused early can only blur a prediction.
+          const int slot = (int)(j & 7);
+          const int64_t first = t - w;                           // first tile of the round
+          const int expect = (int)(ntiles - first < G ? ntiles - first : G);
+          atomicAdd(&racc[slot], prod);
+          __threadfence_block();
+          if (atomicAdd(&rcnt[slot], 1) == expect - 1) {
+            __threadfence_block();
+            const double v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(&racc[slot]), 0ULL));
+            rcnt[slot] = 0;
+            piece_sums[first >> 4] = v;
+            atomicAdd(&chunk_sums[first >> 7], v);
+          }
+        } else {
+          atomicAdd(&piece_sums[t >> 4], prod);
+          atomicAdd(&chunk_sums[t >> 7], prod);
+        }
+      }
+    }
+  }
+}
+
+// Streaming probe (measurement only): the staging half of k_matvec with the consumer removed -- every warp waits
+// for its tile and re-arms the stage at once.  Its GB/s is the ceiling of the TMA stream at this occupancy.
+template <int G, int S>
+__global__ void __launch_bounds__(32 * G, 1)
+k_stream_probe(const double *__restrict__ coefs, const int *__restrict__ cols, const int64_t *__restrict__ tile_base, int64_t ntiles,
+               int64_t nnz_padded, double *__restrict__ sink)
+{
+  constexpr int CAP = MatvecCfg::CAP;
+  constexpr int SLOT = MatvecCfg::SLOT_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char *gbase = smem + (size_t)w * S * SLOT;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
+  uint64_t pol_stream = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  auto issue = [&](int64_t t, int s) -> bool {
+    const int64_t a0 = tile_base[t] & ~3LL;
+    int64_t a1 = (tile_base[t + 1] + 3) & ~3LL;
+    if (a1 > nnz_padded) a1 = nnz_padded;
+    const int64_t n = a1 - a0;
+    if (n <= 0 || n > CAP) return false;
+    mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
+    bulk_g2s_hint(gbase + (size_t)s * SLOT, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
+    bulk_g2s_hint(gbase + (size_t)s * SLOT + CAP * 8, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+    return true;
+  };
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (lane != 0) return;
+  const int64_t stride = (int64_t)gridDim.x * G;
+  int64_t t = (int64_t)blockIdx.x * G + w, ti = t;
+  unsigned armed = 0, phase_bits = 0;
+  for (int s = 0; s < S && ti < ntiles; ++s, ti += stride) if (issue(ti, s)) armed |= 1u << s;
+  double acc = 0.0;
+  for (int64_t j = 0; t < ntiles; ++j, t += stride) {
+    const int s = (int)(j % S);
+    if ((armed >> s) & 1u) {
+      mbar_wait(&bars[s], (phase_bits >> s) & 1u);
+      phase_bits ^= 1u << s;
+      acc += *reinterpret_cast<const double *>(gbase + (size_t)s * SLOT);
+    }
+    armed &= ~(1u << s);
+    if (ti < ntiles) { if (issue(ti, s)) armed |= 1u << s; ti += stride; }
+  }
+  if (acc == 12345.678) *sink = acc;
+}
+
+// plain thread-per-row CSR SpMV in the reference order (validation twin of k_matvec)
+__global__ void k_matvec_simple(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
+                                const int64_t *__restrict__ tile_base, int tr, const double *__restrict__ x, double *__restrict__ y,
+                                int64_t nrows)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int64_t t = r / tr;
+  const int64_t off = tile_base[t] + (int64_t)(uint32_t)(roff[r] - roff[t * tr]);
+  const int len = (int)(uint32_t)(roff[r + 1] - roff[r]);
+  double sum = 0.0;
+  for (int i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[off + i], __ldg(x + cols[off + i])));
+  y[r] = sum;
+}
+
+}  // namespace mfe

@@ -199,99 +199,140 @@ void hs_element(int nx, int ny, int nz, int ex, int ey, int ez, double *K36, dou
 }
 void hs_tables(double *grad192, double *psi64) { hex8_tables(grad192, psi64); }
 
-// The exact-dot pipeline (k_chunk_sums -> k_chunk_prefix -> k_dot_maps -> k_dot_walk) executed sequentially with
-// the same per-thread arithmetic.  stats[0] = dirty leaves, stats[1] = 1 if the whole-vector replay path ran,
-// stats[2] = pieces whose collapsed map failed its check, stats[3] = leaves where the fp and integer map formulations disagree.
+// The exact-dot pipeline (k_chunk_sums -> k_dot_maps -> k_dot_walk) executed sequentially with the same per-thread
+// arithmetic and the same storage conventions (piece maps always stored, leaf maps only for dirty pieces).
+// stats[0] = dirty leaves, stats[1] = 1 if the whole-vector replay path ran, stats[2] = gaps whose collapsed map
+// failed its check, stats[3] = leaves where the fp and integer map formulations disagree.
 double hs_exact_dot(long long n, const double *x, const double *y, long long *stats)
 {
-  const int nchunks = (int)((n + DOT_CHUNK - 1) / DOT_CHUNK);
-  std::vector<double> chunk_sums(nchunks + 1, 0.0), chunk_prefix(nchunks + 2, 0.0);
-  for (int c = 0; c < nchunks; ++c) {      // k_chunk_sums: thread t strides the chunk, warp tree, 8 warp partials
-    double tacc[DOT_CTA_THREADS];
-    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      double acc = 0.0;
-      for (int it = 0; it < DOT_LEAF; ++it) { const long long i = (long long)c * DOT_CHUNK + (long long)it * DOT_CTA_THREADS + t; if (i < n) acc += x[i] * y[i]; }
-      tacc[t] = acc;
-    }
+  const int npieces = (int)((n + DOT_PIECE - 1) / DOT_PIECE);
+  const int nchunks = (npieces + DOT_PIECES_PER_CHUNK - 1) / DOT_PIECES_PER_CHUNK;
+  std::vector<double> chunk_sums(nchunks + 1, 0.0), piece_sums((size_t)nchunks * DOT_PIECES_PER_CHUNK + 1, 0.0);
+  for (int c = 0; c < nchunks; ++c) {      // k_chunk_sums: one warp per piece, lane l strides the piece, shfl_down tree
     double tot = 0.0;
-    for (int w = 0; w < DOT_CTA_THREADS / 32; ++w) {
+    for (int wq = 0; wq < DOT_PIECES_PER_CHUNK; ++wq) {
+      const long long base = ((long long)c * DOT_PIECES_PER_CHUNK + wq) * DOT_PIECE;
       double v[32];
-      for (int l = 0; l < 32; ++l) v[l] = tacc[w * 32 + l];
-      for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < 32; ++l) v[l] += (l + o < 32) ? v[l + o] : 0.0;   // shfl_down tree (lane 0 exact)
+      for (int l = 0; l < 32; ++l) {
+        double acc = 0.0;
+        for (int it = 0; it < DOT_LEAF; ++it) { const long long i = base + it * 32 + l; if (i < n) acc += x[i] * y[i]; }
+        v[l] = acc;
+      }
+      for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < 32; ++l) v[l] += (l + o < 32) ? v[l + o] : 0.0;   // lane 0 exact
+      if (base < n) piece_sums[(size_t)c * DOT_PIECES_PER_CHUNK + wq] = v[0];
       tot += v[0];
     }
     chunk_sums[c] = tot;
   }
-  { double pre = 0.0; for (int c = 0; c < nchunks; ++c) { chunk_prefix[c] = pre; pre += chunk_sums[c]; } chunk_prefix[nchunks] = pre; }
 
   if (stats) stats[3] = 0;
   const int nsupers = (nchunks + 31) / 32, nhypers = (nsupers + 31) / 32;
-  std::vector<DotMap> cta_maps(nchunks + 1), leaf_maps((size_t)(nchunks + 1) * DOT_CTA_THREADS), warp_maps((size_t)(nchunks + 1) * 8),
-      super_maps(nsupers + 1), hyper_maps(nhypers + 1);
+  std::vector<DotMap> cta_maps(nchunks + 1, dot_invalid()), leaf_maps((size_t)(nchunks + 1) * DOT_CTA_THREADS, dot_invalid()),
+      warp_maps((size_t)(nchunks + 1) * 8, dot_invalid()), super_maps(nsupers + 1), hyper_maps(nhypers + 1);
   std::vector<int> dirty_list;
   long long dirty_count = 0;
-  for (int c = 0; c < nchunks; ++c) {      // k_dot_maps
-    const long long base = (long long)c * DOT_CHUNK;
-    double prod[DOT_CTA_THREADS][DOT_LEAF], ls[DOT_CTA_THREADS];
-    int cnt[DOT_CTA_THREADS], hyps[DOT_CTA_THREADS + 1];
-    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      const long long lb = base + (long long)t * DOT_LEAF;
-      cnt[t] = (int)(lb >= n ? 0 : (n - lb < DOT_LEAF ? n - lb : DOT_LEAF));
-      double s = 0.0;
-      for (int i = 0; i < DOT_LEAF; ++i) { prod[t][i] = lb + i < n ? x[lb + i] * y[lb + i] : 0.0; s += prod[t][i]; }
-      ls[t] = s;
-    }
-    // block scan as in the kernel: warp-inclusive (Hillis-Steele), then sequential warp offsets
-    double inc[DOT_CTA_THREADS], wtot[DOT_CTA_THREADS / 32], pres[DOT_CTA_THREADS];
-    for (int w = 0; w < DOT_CTA_THREADS / 32; ++w) {
-      double v[32];
-      for (int l = 0; l < 32; ++l) v[l] = ls[w * 32 + l];
-      for (int o = 1; o < 32; o <<= 1) { double u[32]; for (int l = 0; l < 32; ++l) u[l] = l >= o ? v[l - o] : 0.0; for (int l = 0; l < 32; ++l) if (l >= o) v[l] += u[l]; }
-      for (int l = 0; l < 32; ++l) inc[w * 32 + l] = v[l];
-      wtot[w] = v[31];
-    }
-    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      double woff = 0.0;
-      for (int q = 0; q < t / 32; ++q) woff += wtot[q];
-      const double pre = chunk_prefix[c] + (woff + (inc[t] - ls[t]));
-      pres[t] = pre;
-      hyps[t] = dot_hyp_of(pre);
-    }
-    hyps[DOT_CTA_THREADS] = dot_hyp_of(chunk_prefix[c + 1]);
-    DotMap lm[DOT_CTA_THREADS]; bool any = false; bool dl[DOT_CTA_THREADS];
-    for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-      lm[t] = dot_leaf_map_products_fast(prod[t], cnt[t], hyps[t], pres[t]);
-      {   // the integer formulation must agree (offsets exactly; the fp bounds may only be wider: they are the sums of the
-          // negative / positive offsets when the leaf is far from a binade boundary) wherever usable
-        const DotMap li = dot_leaf_map_products(prod[t], cnt[t], hyps[t]);
-        const bool same = li.hyp == lm[t].hyp && li.a0 == lm[t].a0 && li.a1 == lm[t].a1 && lm[t].lo <= li.lo && lm[t].hi >= li.hi;
-        const bool int_unusable = li.hyp >= 0 && li.hyp != HYP_ZERO && (li.hi >= (1LL << 52) - 16 || li.lo <= -(1LL << 52) + 16 || li.hi - li.lo >= (1LL << 52) - 2);
-        if (!same && !(lm[t].hyp == HYP_INVALID && int_unusable) && stats) { stats[3]++; if (getenv("HS_DEBUG")) fprintf(stderr, "leaf %d cnt %d hyp %d: int(%d %lld %lld %lld %lld) fp(%d %lld %lld %lld %lld)\n", t, cnt[t], hyps[t], li.hyp, li.a0, li.a1, li.lo, li.hi, lm[t].hyp, lm[t].a0, lm[t].a1, lm[t].lo, lm[t].hi); }
+  // k_dot_maps: CTA b owns pieces [b*PP, (b+1)*PP); NT threads build the table of predicted running sums
+  const int NW = 16, NT = 32 * NW, SMS = 148;
+  long long grid = std::min<long long>(SMS, npieces);
+  grid = std::max<long long>(grid, (npieces + 2048 - 1) / 2048);
+  const int PP = npieces ? (int)((npieces + grid - 1) / grid) : 1;
+  grid = npieces ? (npieces + PP - 1) / PP : 0;
+  for (int b = 0; b < (int)grid; ++b) {
+    const int p0 = b * PP, np = std::min(PP, npieces - p0), c0 = p0 / DOT_PIECES_PER_CHUNK;
+    std::vector<double> table(np + 1);
+    {
+      double warp_part[NW], warp_run[NW], inc_t[NT], run_t[NT];
+      const int R = (np + NT - 1) / NT;
+      for (int wq = 0; wq < NW; ++wq) {
+        double part[32], v[32];
+        for (int l = 0; l < 32; ++l) {
+          const int tid = wq * 32 + l;
+          double pt = 0.0;
+          for (int i = tid; i < c0; i += NT) pt += chunk_sums[i];
+          if (tid < p0 - c0 * DOT_PIECES_PER_CHUNK) pt += piece_sums[(size_t)c0 * DOT_PIECES_PER_CHUNK + tid];
+          part[l] = pt;
+          double run = 0.0;
+          for (int q = 0; q < R; ++q) if (tid * R + q < np) run += piece_sums[(size_t)p0 + tid * R + q];
+          run_t[tid] = run; v[l] = run;
+        }
+        for (int o = 16; o > 0; o >>= 1) { double u[32]; for (int l = 0; l < 32; ++l) u[l] = part[l ^ o]; for (int l = 0; l < 32; ++l) part[l] += u[l]; }
+        warp_part[wq] = part[0];
+        for (int o = 1; o < 32; o <<= 1) { double u[32]; for (int l = 0; l < 32; ++l) u[l] = l >= o ? v[l - o] : 0.0; for (int l = 0; l < 32; ++l) if (l >= o) v[l] += u[l]; }
+        for (int l = 0; l < 32; ++l) inc_t[wq * 32 + l] = v[l];
+        warp_run[wq] = v[31];
       }
-      dl[t] = cnt[t] > 0 && (lm[t].hyp == HYP_INVALID || hyps[t] != hyps[t + 1]);
-      any = any || dl[t];
+      double B0 = 0.0;
+      for (int q = 0; q < NW; ++q) B0 += warp_part[q];
+      for (int tid = 0; tid < NT; ++tid) {
+        double woff = 0.0;
+        for (int q = 0; q < tid / 32; ++q) woff += warp_run[q];
+        double acc = woff + (inc_t[tid] - run_t[tid]);
+        for (int q = 0; q < R; ++q) if (tid * R + q < np) { table[tid * R + q] = B0 + acc; acc += piece_sums[(size_t)p0 + tid * R + q]; }
+        if (tid == NT - 1) table[np] = B0 + acc;
+      }
     }
+    for (int j = 0; j < np; ++j) {          // one warp per piece
+      const int piece = p0 + j;
+      double prod[32][DOT_LEAF], ordered[32][DOT_LEAF], ls[32], inc[32], pres[32];
+      int cnt[32], hyps[33];
+      for (int l = 0; l < 32; ++l) {
+        const long long lb = (long long)piece * DOT_PIECE + (long long)l * DOT_LEAF;
+        cnt[l] = (int)(lb >= n ? 0 : (n - lb < DOT_LEAF ? n - lb : DOT_LEAF));
+        for (int i = 0; i < DOT_LEAF; ++i) ordered[l][i] = lb + i < n ? x[lb + i] * y[lb + i] : 0.0;
+        const int rot = cnt[l] == DOT_LEAF ? (l & (DOT_LEAF - 1)) : 0;      // full leaves are visited in the rotated order
+        double sacc = 0.0;
+        for (int i = 0; i < DOT_LEAF; ++i) { prod[l][i] = ordered[l][i ^ rot]; sacc += prod[l][i]; }
+        ls[l] = sacc; inc[l] = sacc;
+      }
+      for (int o = 1; o < 32; o <<= 1) { double u[32]; for (int l = 0; l < 32; ++l) u[l] = l >= o ? inc[l - o] : 0.0; for (int l = 0; l < 32; ++l) if (l >= o) inc[l] += u[l]; }
+      for (int l = 0; l < 32; ++l) { pres[l] = table[j] + (inc[l] - ls[l]); hyps[l] = dot_hyp_of(pres[l]); }
+      hyps[32] = dot_hyp_of(table[j + 1]);
+      DotMap lm[32]; bool dl[32]; bool any = false;
+      for (int l = 0; l < 32; ++l) {
+        const int hyp = hyps[l];
+        bool risky = false;
+        DotMap m = dot_identity();
+        if (cnt[l] == DOT_LEAF && hyp >= 0 && hyp != HYP_ZERO) {
+          double sa, slo, shi;
+          if (dot_leaf16_simple(prod[l], hyp, pres[l], sa, slo, shi)) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
+          else { m = dot_leaf_map16_fp(ordered[l], hyp); risky = dot_leaf_risky(m, hyp, pres[l]); }
+        } else if (cnt[l] == DOT_LEAF) m = dot_leaf_map16(prod[l], hyp, pres[l]);
+        else if (cnt[l] > 0) { const long long lb = (long long)piece * DOT_PIECE + (long long)l * DOT_LEAF; m = dot_leaf_map(x, y, lb, lb + cnt[l], hyp); }
+        lm[l] = m;
+        if (cnt[l] > 0) {   // the integer formulation must agree (offsets exactly; the fp bounds may only be wider: they are the sums of the
+                            // negative / positive offsets when the leaf is far from a binade boundary) wherever usable
+          const DotMap li = dot_leaf_map_products(ordered[l], cnt[l], hyp);
+          const bool same = li.hyp == m.hyp && li.a0 == m.a0 && li.a1 == m.a1 && m.lo <= li.lo && m.hi >= li.hi;
+          const bool int_unusable = li.hyp >= 0 && li.hyp != HYP_ZERO && (li.hi >= (1LL << 52) - 16 || li.lo <= -(1LL << 52) + 16 || li.hi - li.lo >= (1LL << 52) - 2);
+          if (!same && !(m.hyp == HYP_INVALID && int_unusable) && stats) { stats[3]++; if (getenv("HS_DEBUG")) fprintf(stderr, "piece %d leaf %d cnt %d hyp %d: int(%d %lld %lld %lld %lld) fp(%d %lld %lld %lld %lld)\n", piece, l, cnt[l], hyp, li.hyp, li.a0, li.a1, li.lo, li.hi, m.hyp, m.a0, m.a1, m.lo, m.hi); }
+        }
+        dl[l] = cnt[l] > 0 && (m.hyp == HYP_INVALID || hyps[l] != hyps[l + 1] || risky);
+        any = any || dl[l];
+      }
+      DotMap wm = dot_identity();
+      for (int l = 0; l < 32; ++l) wm = dot_compose(wm, lm[l]);
+      if (any) {
+        for (int l = 0; l < 32; ++l) {
+          leaf_maps[(size_t)piece * 32 + l] = lm[l];
+          if (dl[l]) { if (dirty_count < DOT_MAX_DIRTY) dirty_list.push_back(piece * 32 + l); ++dirty_count; }
+        }
+      }
+      wm.pad = any ? 1 : 0;
+      warp_maps[piece] = wm;
+    }
+  }
+  for (int c = 0; c < nchunks; ++c) {
     DotMap cm = dot_identity();
-    for (int t = 0; t < DOT_CTA_THREADS; ++t) cm = dot_compose(cm, lm[t]);
-    if (any) {
-      for (int t = 0; t < DOT_CTA_THREADS; ++t) {
-        leaf_maps[(size_t)c * DOT_CTA_THREADS + t] = lm[t];
-        if (dl[t]) { if (dirty_count < DOT_MAX_DIRTY) dirty_list.push_back(c * DOT_CTA_THREADS + t); ++dirty_count; }
-      }
-      for (int wq = 0; wq < 8; ++wq) { DotMap wm = dot_identity(); for (int l = 0; l < 32; ++l) wm = dot_compose(wm, lm[wq * 32 + l]); warp_maps[(size_t)c * 8 + wq] = wm; }
-      cm = dot_invalid(); cm.pad = 1;
-    } else {
-      for (int t = 0; t < DOT_CTA_THREADS; ++t) leaf_maps[(size_t)c * DOT_CTA_THREADS + t] = dot_invalid();   // not stored on the device
-      for (int wq = 0; wq < 8; ++wq) warp_maps[(size_t)c * 8 + wq] = dot_invalid();
-    }
+    for (int q = 0; q < DOT_PIECES_PER_CHUNK; ++q) if (c * DOT_PIECES_PER_CHUNK + q < npieces) { DotMap u = warp_maps[(size_t)c * DOT_PIECES_PER_CHUNK + q]; u.pad = 0; cm = dot_compose(cm, u); }
+    cm.pad = 1;
     cta_maps[c] = cm;
   }
-  for (int sg = 0; sg < nsupers; ++sg) { DotMap m = dot_identity(); for (int i = sg * 32; i < std::min(nchunks, sg * 32 + 32); ++i) m = dot_compose(m, cta_maps[i]); m.pad = 0; super_maps[sg] = m; }
+  for (int sg = 0; sg < nsupers; ++sg) { DotMap m = dot_identity(); for (int i = sg * 32; i < std::min(nchunks, sg * 32 + 32); ++i) { DotMap u = cta_maps[i]; u.pad = 0; m = dot_compose(m, u); } m.pad = 0; super_maps[sg] = m; }
   for (int hg = 0; hg < nhypers; ++hg) { DotMap m = dot_identity(); for (int i = hg * 32; i < std::min(nsupers, hg * 32 + 32); ++i) m = dot_compose(m, super_maps[i]); hyper_maps[hg] = m; }
   if (stats) { stats[0] = dirty_count; stats[1] = 0; stats[2] = 0; }
   if (dirty_count > DOT_MAX_DIRTY) { if (stats) stats[1] = 1; return dot_replay(x, y, 0, n, 0.0); }
   // k_dot_walk
-  const int D = (int)dirty_count; const long long nleaves = (long long)nchunks * DOT_CTA_THREADS;
+  const int D = (int)dirty_count; const long long nleaves = (long long)npieces * 32;
   std::vector<int> sorted(dirty_list);
   std::sort(sorted.begin(), sorted.end());
   DotWork w{};

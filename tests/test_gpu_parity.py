@@ -123,22 +123,20 @@ def test_matvec_bit_exact(n, oracle_built, product_lib):
         assert_bits(y, o.matvec(x), "matvec trial %d" % trial)
 
 
-@pytest.mark.parametrize("line_tiles", [-1, 0, 1, 3])
-def test_matvec_every_configuration_bit_exact(line_tiles, oracle_built, product_lib):
-    """All SpMV kernel configurations (legacy group kernel 0-9, warp-per-tile kernel 10-21) and tile orders give the
-    reference's bits; 40x33x21 has x-lines of 41 nodes so tiles straddle lines, faces and the last partial tile."""
+def test_matvec_every_configuration_bit_exact(oracle_built, product_lib):
+    """All SpMV kernel configurations (warps per CTA, stages, gather batches) give the reference's bits; 40x33x21 has
+    x-lines of 41 nodes so tiles straddle lines, faces and the last partial tile."""
     n = (40, 33, 21)
     o = Oracle(*n).setup()
     p = Problem(*n).setup()
     rng = np.random.default_rng(11)
     x = rng.standard_normal(o.nrows()) * 10.0 ** rng.integers(-3, 4, o.nrows())
     want = o.matvec(x)
-    p.mesh.set_option("matvec_line_tiles", line_tiles)
-    for cfg in range(22):
+    for cfg in range(10):
         p.mesh.set_option("matvec_config", cfg)
         y = np.full(o.nrows(), 123.0)
         mf.matvec(p.A, x, y)
-        assert_bits(y, want, "matvec config %d line_tiles %d" % (cfg, line_tiles))
+        assert_bits(y, want, "matvec config %d" % cfg)
 
 
 def test_matvec_imported_csr_ragged(product_lib):

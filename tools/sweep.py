@@ -9,7 +9,7 @@ import minife_b200 as mf
 ap = argparse.ArgumentParser()
 ap.add_argument("--nx", type=int, default=256)
 ap.add_argument("--reps", type=int, default=20)
-ap.add_argument("--configs", default="0,1,2,3,4,5,6,7,8,9")
+ap.add_argument("--configs", default="0")
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--flags", default="1")
 ap.add_argument("--line-tiles", default="-1")
@@ -27,23 +27,19 @@ print(json.dumps({"setup": {p: mesh.phase_ms(p) for p in ("structure", "assembly
 mvb = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N
 for cfg in [int(c) for c in args.configs.split(",") if c != ""]:
     mesh.set_option("matvec_config", cfg)
-    for fl in [int(f) for f in args.flags.split(",")]:
-        mesh.set_option("matvec_flags", fl)
-        for lt in [int(v) for v in args.line_tiles.split(",")]:
-            if cfg < 10 and lt != int(args.line_tiles.split(",")[0]):
-                continue
-            mesh.set_option("matvec_line_tiles", lt)
-            for what in ("matvec", "matvec_dot"):
-                ms = mesh.time_kernel(what, args.reps)
-                print(json.dumps({"kernel": what, "config": cfg, "flags": fl, "line_tiles": lt, "ms": ms, "GBs": mvb / ms / 1e6}), flush=True)
-mesh.set_option("matvec_config", 10)
-mesh.set_option("matvec_flags", 1)
-mesh.set_option("matvec_line_tiles", -1)
+    for fl in (0,):
+        for what in ("matvec", "matvec_dot"):
+            ms = mesh.time_kernel(what, args.reps)
+            print(json.dumps({"kernel": what, "config": cfg, "ms": ms, "GBs": mvb / ms / 1e6}), flush=True)
+mesh.set_option("matvec_config", 0)
 for what, byts in (("stream_probe", 12.0 * nnz), ("stream_probe21", 12.0 * nnz), ("matvec_simple", mvb), ("waxpby", 24.0 * N), ("xr_update", 48.0 * N), ("dot_rr", 8.0 * N), ("dot_pap", 16.0 * N)):
     for mode in ((0, 1, 2) if what.startswith("dot") else (0,)):
         if mode == 1 and n > 64:
             continue
         mesh.set_dot_mode(mode)
-        ms = mesh.time_kernel(what, args.reps)
-        print(json.dumps({"kernel": what, "dot_mode": mode, "ms": ms, "GBs": byts / ms / 1e6}))
+        for nw in ((16, 24) if (what.startswith("dot") and mode == 0) else (0,)):
+            mesh.set_option("dot_maps_warps", nw)
+            ms = mesh.time_kernel(what, args.reps)
+            print(json.dumps({"kernel": what, "dot_mode": mode, "dot_maps_warps": nw, "ms": ms, "GBs": byts / ms / 1e6}), flush=True)
+mesh.set_option("dot_maps_warps", 0)
 mesh.close()
