@@ -187,6 +187,9 @@ def main():
     ap.add_argument("--cpu-nx", type=int, default=128, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dot-mode", type=int, default=0)
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange and dot all-reduce over NVLink peer stores "
+                    "(default; falls back to NCCL when CUDA IPC is unavailable) or over NCCL send/recv + allgather")
+    ap.add_argument("--no-overlap", action="store_true", help="peer mode: do not overlap the halo exchange with the interior SpMV tiles")
     ap.add_argument("--op-timing", type=int, default=2, help="CUDA events inside the timed solves: 2 = around every SpMV launch (roofline), 1 = every op class, 0 = none")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -221,6 +224,8 @@ def main():
         mesh.comm_init(bytes(idt.cpu().numpy().tobytes()))
     mesh.set_dot_mode(args.dot_mode)
     mesh.set_op_timing(args.op_timing)
+    mesh.set_option("comm_mode", 1 if args.comm == "peer" else 0)
+    mesh.set_option("overlap", 0 if args.no_overlap else 1)
 
     A = mf.CSRMatrix()
     t_setup = time.time()
@@ -338,6 +343,8 @@ def main():
             "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "miniFE %dx%dx%d hex8 Poisson (%d^3 elements per GPU), assembled on device, 200-iteration unpreconditioned CG" % (dims[0], dims[1], dims[2], args.nx),
                        "rows": nrows_g, "nnz": nnz_g, "cg_iterations": iters, "final_resid": normr, "parallelism": "box_partition x%d, 1 rank per GPU" % world,
+                       "comm": (None if world == 1 else ("NCCL send/recv + allgather" if args.comm == "nccl" else
+                                "NVLink peer stores (halo + dot all-reduce)%s" % ("" if args.no_overlap else ", halo overlapped with the interior SpMV tiles"))),
                        "l2": "inputs larger than L2 (7.4 GB per iteration vs 126 MB)", "dot": ["exact (order-reproducing)", "serial", "tree"][args.dot_mode],
                        "flop_model": "ref/src/driver.hpp:322-341"},
             "hbm_gbs": hbm_gbs, "hbm_gbs_per_gpu": hbm_gbs / world, "pct_of_8TBs_per_gpu": 100.0 * hbm_gbs / world / 8000.0,

@@ -59,7 +59,7 @@ struct NcclApi {
   const char *(*GetErrorString)(int) = nullptr;
 };
 static NcclApi g_nccl;
-enum { NCCL_FLOAT64 = 8, NCCL_INT32 = 2 };   // ncclDataType_t values (nccl.h)
+enum { NCCL_FLOAT64 = 8, NCCL_INT32 = 2, NCCL_INT8 = 0 };   // ncclDataType_t values (nccl.h)
 static const char *nccl_errstr(int r) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"; }
 static int nccl_load()
 {
@@ -84,6 +84,18 @@ struct DotWs {                  // workspace of the exact dot (sized for nrows)
   DotWork w{};                  // w.chunk_sums / w.piece_sums are set per launch to one of the two pairs below
   double *chunk_sums_a = nullptr, *piece_sums_a = nullptr;   // written by k_xr_update (r.r) and k_chunk_sums
   double *chunk_sums_b = nullptr, *piece_sums_b = nullptr;   // accumulated by the SpMV (p.Ap), zeroed by k_xr_update
+};
+
+// NVLink peer-memory communicator (peer.cuh): one mailbox per rank, opened by every other rank through CUDA IPC
+struct PeerComm {
+  bool ok = false;                 // every rank exported its mailbox and opened all the others
+  void *mailbox = nullptr;         // my mailbox (cudaMalloc)
+  std::vector<void *> base;        // base[p]: rank p's mailbox in my address space (base[rank] = mailbox)
+  std::vector<int64_t> halo_cap;   // per rank: capacity (doubles) of one halo buffer
+  size_t off_flags = 0, off_halo = 0;
+  unsigned long long halo_epoch = 0, dot_epoch = 0;
+  unsigned int *d_ticket = nullptr;
+  int *d_err = nullptr;
 };
 
 struct mfe_ctx {
@@ -129,12 +141,20 @@ struct mfe_ctx {
 
   // comm
   ncclComm_t_ comm = nullptr;
+  PeerComm peer;
+  int comm_mode = 1;             // 1: NVLink peer stores when available (default), 0: NCCL send/recv + allgather
+  int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
+  int64_t peer_timeout_ms = 30000;
+  std::vector<int> send_dst_offset;
+  int *d_tiles_interior = nullptr, *d_tiles_boundary = nullptr;   // SpMV tiles without / with external columns
+  int64_t n_interior = 0, n_boundary = 0;
 
   // phase timings (ms)
   double t_structure = 0, t_assembly = 0, t_assembly_elem = 0, t_assembly_gather = 0, t_dir0 = 0, t_dir1 = 0, t_make_local = 0, t_cg = 0;
 };
 
 static int free_dev(void *p) { if (p) cudaFree(p); return 0; }
+static void peer_teardown(mfe_ctx *c);
 
 template <typename T>
 static int dev_alloc(T **p, int64_t n)
@@ -271,7 +291,9 @@ extern "C" void mfe_destroy(mfe_ctx *c)
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  peer_teardown(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  free_dev(c->d_tiles_interior); free_dev(c->d_tiles_boundary);
   free_matrix(c); free_vectors(c);
   free_dev(c->d_boxes); free_dev(c->d_sc); free_dev(c->d_hist); free_dev(c->d_gather);
   free_dev(c->d_elements_to_send); free_dev(c->d_send_buf);
@@ -288,6 +310,95 @@ extern "C" int mfe_comm_unique_id(char id128[128])
   memcpy(id128, id.internal, 128);
   return 0;
 }
+// Mailbox layout (peer.cuh): dot slots [2][nranks] | halo flags [nranks] | halo data [2][halo_cap(rank)]
+static int64_t halo_cap_of(const RankBox &b)
+{
+  const int64_t lx = b.nb[1] - b.nb[0], ly = b.nb[3] - b.nb[2], lz = b.nb[5] - b.nb[4];
+  return (lx + 2) * (ly + 2) * (lz + 2) - lx * ly * lz + 8;      // the one-node shell bounds the externals
+}
+static DotSlot *peer_dot_slots(mfe_ctx *c, int p) { return reinterpret_cast<DotSlot *>(c->peer.base[p]); }
+static unsigned long long *peer_halo_flags(mfe_ctx *c, int p) { return reinterpret_cast<unsigned long long *>((char *)c->peer.base[p] + c->peer.off_flags); }
+static double *peer_halo_buf(mfe_ctx *c, int p, unsigned long long epoch)
+{
+  return reinterpret_cast<double *>((char *)c->peer.base[p] + c->peer.off_halo) + (epoch & 1ULL) * c->peer.halo_cap[p];
+}
+
+static void peer_teardown(mfe_ctx *c)
+{
+  PeerComm &P = c->peer;
+  for (size_t p = 0; p < P.base.size(); ++p)
+    if ((int)p != c->rank && P.base[p]) cudaIpcCloseMemHandle(P.base[p]);
+  P.base.clear();
+  if (P.ok && c->comm && c->d_gather) {
+    // exported memory must outlive every importer's mapping: all ranks close first (mfe_destroy is collective
+    // for nranks > 1, like MPI_Finalize), then free
+    g_nccl.AllGather(c->dot.w.result ? (const void *)c->dot.w.result : (const void *)c->d_sc, c->d_gather, 1, NCCL_FLOAT64, c->comm, c->stream);
+    cudaStreamSynchronize(c->stream);
+  }
+  free_dev(P.mailbox); free_dev(P.d_ticket); free_dev(P.d_err);
+  P.mailbox = nullptr; P.d_ticket = nullptr; P.d_err = nullptr; P.ok = false;
+  cudaGetLastError();
+}
+
+// Collective over the NCCL communicator: export my mailbox, gather every rank's IPC handle, open them.  Any failure
+// on any rank (no IPC in this container, no peer access, ...) leaves peer.ok = false on ALL ranks -> NCCL path.
+static int peer_setup(mfe_ctx *c)
+{
+  PeerComm &P = c->peer;
+  const int np = c->nranks;
+  P.ok = false;
+  if (np > PEER_MAX_RANKS || getenv("MFE_NO_PEER")) return 0;      // the same decision on every rank
+  P.halo_cap.resize(np);
+  for (int p = 0; p < np; ++p) P.halo_cap[p] = halo_cap_of(c->boxes[p]);
+  P.off_flags = ((size_t)2 * np * sizeof(DotSlot) + 255) & ~(size_t)255;
+  P.off_halo = (P.off_flags + (size_t)np * 8 + 255) & ~(size_t)255;
+  const size_t bytes = P.off_halo + (size_t)2 * P.halo_cap[c->rank] * 8;
+  int local_ok = 1;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (cudaMalloc(&P.mailbox, bytes) != cudaSuccess || cudaMalloc((void **)&P.d_ticket, 4) != cudaSuccess || cudaMalloc((void **)&P.d_err, 4) != cudaSuccess) local_ok = 0;
+  if (local_ok) {
+    cudaMemsetAsync(P.mailbox, 0, bytes, c->stream);
+    cudaMemsetAsync(P.d_ticket, 0, 4, c->stream);
+    cudaMemsetAsync(P.d_err, 0, 4, c->stream);
+    if (cudaIpcGetMemHandle(&mine, P.mailbox) != cudaSuccess) local_ok = 0;
+  }
+  cudaGetLastError();
+  // gather {handle, ok} of every rank (the mailboxes are zeroed before anybody can learn their address)
+  struct Rec { cudaIpcMemHandle_t h; int ok; int pad[3]; };
+  static_assert(sizeof(Rec) == 80, "Rec layout");
+  Rec rec; rec.h = mine; rec.ok = local_ok; rec.pad[0] = rec.pad[1] = rec.pad[2] = 0;
+  Rec *d_one = nullptr, *d_all = nullptr;
+  if (dev_alloc(&d_one, 1) || dev_alloc(&d_all, np)) return 1;
+  std::vector<Rec> all(np);
+  CK(cudaMemcpyAsync(d_one, &rec, sizeof rec, cudaMemcpyHostToDevice, c->stream));
+  CKN(g_nccl.AllGather(d_one, d_all, sizeof(Rec), NCCL_INT8, c->comm, c->stream));
+  CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * np, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  bool everybody = true;
+  for (int p = 0; p < np; ++p) everybody = everybody && all[p].ok == 1;
+  P.base.assign(np, nullptr);
+  int open_ok = everybody ? 1 : 0;
+  if (everybody) {
+    for (int p = 0; p < np; ++p) {
+      if (p == c->rank) { P.base[p] = P.mailbox; continue; }
+      if (cudaIpcOpenMemHandle(&P.base[p], all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { P.base[p] = nullptr; open_ok = 0; cudaGetLastError(); }
+    }
+  }
+  // second round: did every rank open every mailbox?
+  rec.ok = open_ok;
+  CK(cudaMemcpyAsync(d_one, &rec, sizeof rec, cudaMemcpyHostToDevice, c->stream));
+  CKN(g_nccl.AllGather(d_one, d_all, sizeof(Rec), NCCL_INT8, c->comm, c->stream));
+  CK(cudaMemcpyAsync(all.data(), d_all, sizeof(Rec) * np, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_one); cudaFree(d_all);
+  bool all_open = true;
+  for (int p = 0; p < np; ++p) all_open = all_open && all[p].ok == 1;
+  if (!all_open) { peer_teardown(c); return 0; }
+  P.ok = true;
+  return 0;
+}
+
 extern "C" int mfe_comm_init(mfe_ctx *c, const char id128[128])
 {
   if (!c) return fail("null context");
@@ -297,7 +408,7 @@ extern "C" int mfe_comm_init(mfe_ctx *c, const char id128[128])
   ncclUniqueId_t id;
   memcpy(id.internal, id128, 128);
   CKN(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank));
-  return 0;
+  return peer_setup(c);
 }
 
 // vectors + dot workspace sized for (nrows, ncols)
@@ -462,6 +573,33 @@ extern "C" int mfe_impose_dirichlet(mfe_ctx *c, double val, int which)
 // externals appear in ascending global row.  So external_index = externals sorted by (first(E), globalrow(E)).
 // The peers' lists (-> elements_to_send) follow from the same rule applied to the peer's box: no messages.
 // ---------------------------------------------------------------------------------------------------------
+// SpMV tiles that touch an external column (boundary) and those that do not (interior): the interior pass needs
+// no halo, so it runs while the neighbours' stores are in flight (the reference's matvec_overlap idea,
+// SparseMatrix_functions.hpp:624-675, without re-ordering the matrix: whole rows stay intact and bit-exact).
+static int classify_tiles(mfe_ctx *c)
+{
+  free_dev(c->d_tiles_interior); free_dev(c->d_tiles_boundary);
+  c->d_tiles_interior = c->d_tiles_boundary = nullptr; c->n_interior = c->n_boundary = 0;
+  if (c->ntiles <= 0 || c->ntiles > 0x7fffffffLL) return 0;
+  unsigned char *d_flag = nullptr;
+  if (dev_alloc(&d_flag, c->ntiles)) return 1;
+  k_classify_tiles<<<grid_for(c->ntiles * 32, 256), 256, 0, c->stream>>>(c->d_cols, c->d_tile_base, c->ntiles, (int)c->nrows, d_flag);
+  c->launches++;
+  std::vector<unsigned char> flag(c->ntiles);
+  CK(cudaMemcpyAsync(flag.data(), d_flag, c->ntiles, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_flag);
+  std::vector<int> in, bd;
+  in.reserve(c->ntiles);
+  for (int64_t t = 0; t < c->ntiles; ++t) (flag[t] ? bd : in).push_back((int)t);
+  c->n_interior = (int64_t)in.size(); c->n_boundary = (int64_t)bd.size();
+  if (dev_alloc(&c->d_tiles_interior, c->n_interior + 1) || dev_alloc(&c->d_tiles_boundary, c->n_boundary + 1)) return 1;
+  if (!in.empty()) CK(cudaMemcpyAsync(c->d_tiles_interior, in.data(), sizeof(int) * in.size(), cudaMemcpyHostToDevice, c->stream));
+  if (!bd.empty()) CK(cudaMemcpyAsync(c->d_tiles_boundary, bd.data(), sizeof(int) * bd.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
 {
   if (!c || !c->has_structure) return fail("mfe_make_local_matrix: no matrix");
@@ -483,7 +621,9 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   c->external_index = L.external_index; c->external_local_index = L.external_local_index;
   c->elements_to_send = L.elements_to_send; c->neighbors = L.neighbors;
   c->recv_length = L.recv_length; c->send_length = L.send_length;
+  c->send_dst_offset = L.send_dst_offset;
   c->num_cols = L.num_cols;
+  if (c->neighbors.size() > PEER_MAX_NEIGHBORS) return fail("mfe_make_local_matrix: %d neighbours (> %d)", (int)c->neighbors.size(), (int)PEER_MAX_NEIGHBORS);
   const int n_ext = (int)c->external_index.size();
   // device: rewrite the columns (owned: col - start_row; external: external_local_index)
   std::vector<std::pair<int, int>> srt(n_ext);
@@ -503,6 +643,7 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   if (dev_alloc(&c->d_elements_to_send, nsend + 1) || dev_alloc(&c->d_send_buf, nsend + 1)) return 1;
   CK(cudaMemcpyAsync(c->d_elements_to_send, c->elements_to_send.data(), sizeof(int) * nsend, cudaMemcpyHostToDevice, c->stream));
   if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  if (classify_tiles(c)) return 1;
   c->t_make_local = tm.stop();
   cudaFree(d_sg); cudaFree(d_sl);
   CK(cudaGetLastError());
@@ -520,7 +661,7 @@ static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {12,
 enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
 
 template <int G, int S, int H>
-static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k)
+static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork)
 {
   static bool attr_set[64] = { false };
   const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 64;
@@ -529,35 +670,39 @@ static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_s
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[c->device & 63] = true;
   }
-  const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (c->ntiles + G - 1) / G));
+  if (!tile_list) nwork = c->ntiles;
+  if (nwork <= 0) return 0;
+  const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (nwork + G - 1) / G));
   kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, 0,
-                                          with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k);
+                                          with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork);
   c->launches++;
   return 0;
 }
 
-static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k)
+static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k,
+                               const int *tile_list = nullptr, int64_t nwork = 0)
 {
   switch (c->mv_cfg) {
-    case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k);
-    case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k);
-    case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k);
-    case 3: return launch_matvec_cfg<12, 1, 1>(c, x, y, with_sums, gate, k);
-    case 4: return launch_matvec_cfg<14, 1, 1>(c, x, y, with_sums, gate, k);
-    case 5: return launch_matvec_cfg<18, 1, 2>(c, x, y, with_sums, gate, k);
-    case 6: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k);
-    case 7: return launch_matvec_cfg<21, 1, 2>(c, x, y, with_sums, gate, k);
-    case 8: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k);
-    case 9: return launch_matvec_cfg<20, 1, 3>(c, x, y, with_sums, gate, k);
+    case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 3: return launch_matvec_cfg<12, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 4: return launch_matvec_cfg<14, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 5: return launch_matvec_cfg<18, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 6: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 7: return launch_matvec_cfg<21, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 8: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 9: return launch_matvec_cfg<20, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork);
   }
   return fail("bad matvec configuration %d", c->mv_cfg);
 }
 
 // halo exchange on the context stream: ref/src/exchange_externals.hpp:44-161
-static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+static bool use_peer(const mfe_ctx *c) { return c->nranks > 1 && c->comm_mode == 1 && c->peer.ok; }
+
+// NCCL path: pack + grouped send/recv per neighbour (complete when the stream reaches the next kernel)
+static int exchange_nccl(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 {
-  if (c->nranks == 1) return 0;
-  if (!c->comm) return fail("exchange_externals: nranks > 1 but mfe_comm_init was not called");
   const int nsend = (int)c->elements_to_send.size();
   if (nsend > 0) { k_pack<<<grid_for(nsend, 256), 256, 0, c->stream>>>(x, c->d_elements_to_send, nsend, c->d_send_buf, gate, k); c->launches++; }
   CKN(g_nccl.GroupStart());
@@ -571,9 +716,63 @@ static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
   return 0;
 }
 
+// first half: peer mode stores my boundary values into the neighbours' halo buffers; NCCL mode does everything
+static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+{
+  if (c->nranks == 1) return 0;
+  if (!c->comm) return fail("exchange_externals: nranks > 1 but mfe_comm_init was not called");
+  if (!use_peer(c)) return exchange_nccl(c, x, gate, k);
+  const unsigned long long epoch = ++c->peer.halo_epoch;
+  const int nsend = (int)c->elements_to_send.size();
+  if (nsend == 0) return 0;
+  PeerHalo ph{};
+  int n = 0, so = 0;
+  for (size_t i = 0; i < c->neighbors.size(); ++i) {
+    if (c->send_length[i] <= 0) continue;
+    const int p = c->neighbors[i];
+    ph.start[n] = so;
+    ph.dst[n] = peer_halo_buf(c, p, epoch) + c->send_dst_offset[i];
+    ph.flag[n] = peer_halo_flags(c, p) + c->rank;
+    so += c->send_length[i]; ++n;
+  }
+  ph.start[n] = so; ph.n = n;
+  k_pack_peer<<<grid_for(nsend, 256), 256, 0, c->stream>>>(x, c->d_elements_to_send, nsend, ph, epoch, c->peer.d_ticket, gate, k);
+  c->launches++;
+  return 0;
+}
+// second half (peer mode): wait for the neighbours' stores of this epoch and fill the external tail of x
+static int exchange_end(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+{
+  if (!use_peer(c)) return 0;
+  const int n_ext = (int)(c->num_cols - c->nrows);
+  if (n_ext <= 0) return 0;
+  const unsigned long long epoch = c->peer.halo_epoch;
+  PeerWait pw{};
+  int n = 0;
+  for (size_t i = 0; i < c->neighbors.size(); ++i)
+    if (c->recv_length[i] > 0) pw.flag[n++] = peer_halo_flags(c, c->rank) + c->neighbors[i];
+  pw.n = n;
+  const int grid = std::max(1, std::min(32, (n_ext + 2047) / 2048));
+  k_halo_wait_copy<<<grid, 256, 0, c->stream>>>(pw, epoch, peer_halo_buf(c, c->rank, epoch), x + c->nrows, n_ext,
+                                                (unsigned long long)c->peer_timeout_ms * 1000000ULL, c->peer.d_err, gate, k);
+  c->launches++;
+  return 0;
+}
+static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+{
+  if (exchange_begin(c, x, gate, k)) return 1;
+  return exchange_end(c, x, gate, k);
+}
+
 static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k)
 {
-  if (exchange(c, x, gate, k)) return 1;
+  if (exchange_begin(c, x, gate, k)) return 1;
+  if (use_peer(c) && c->overlap && c->n_interior > 0 && c->n_boundary > 0) {
+    if (launch_matvec_local(c, x, y, with_sums, gate, k, c->d_tiles_interior, c->n_interior)) return 1;   // needs no halo
+    if (exchange_end(c, x, gate, k)) return 1;
+    return launch_matvec_local(c, x, y, with_sums, gate, k, c->d_tiles_boundary, c->n_boundary);
+  }
+  if (exchange_end(c, x, gate, k)) return 1;
   return launch_matvec_local(c, x, y, with_sums, gate, k);
 }
 
@@ -625,10 +824,19 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
   double *nh = hist, *rh = hist ? hist + c->hist_cap : nullptr, *ph = hist ? hist + 2 * c->hist_cap : nullptr, *ah = hist ? hist + 3 * c->hist_cap : nullptr;
   const int nchunks = (int)((n + DOT_CHUNK - 1) / DOT_CHUNK);
   const bool multi = c->nranks > 1;
+  const bool peer = use_peer(c);
+  if (multi && !c->comm) return fail("dot: nranks > 1 but mfe_comm_init was not called");
   const int epi_local = multi ? EPI_NONE : epi;
+  PeerDot pd{};                                   // nranks == 0: no peer all-reduce inside the kernel
+  if (peer) {
+    pd.nranks = c->nranks; pd.rank = c->rank; pd.epoch = ++c->peer.dot_epoch;
+    pd.timeout_ns = (unsigned long long)c->peer_timeout_ms * 1000000ULL; pd.err = c->peer.d_err;
+    for (int p = 0; p < c->nranks; ++p) pd.box[p] = peer_dot_slots(c, p);
+  }
   DotWork w = c->dot.w;
   w.chunk_sums = sums_kind == 2 ? c->dot.chunk_sums_b : c->dot.chunk_sums_a;
   w.piece_sums = sums_kind == 2 ? c->dot.piece_sums_b : c->dot.piece_sums_a;
+  bool finished = false;                          // global sum + epilogue already done by the local kernel
   if (c->dot_mode == MFE_DOT_SERIAL) {
     k_dot_serial<<<1, 1, 0, c->stream>>>(n, x, y, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
     c->launches++;
@@ -640,12 +848,15 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
       c->launches += 2;
     } else {
       if (launch_dot_maps(c, n, x, y, w, gate, k)) return 1;
-      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, sc, epi_local, k, nh, rh, ph, ah, gate);
+      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, sc, peer ? epi : epi_local, k, nh, rh, ph, ah, gate, pd);
       c->launches++;
+      finished = peer;
     }
   }
-  if (multi) {
-    if (!c->comm) return fail("dot: nranks > 1 but mfe_comm_init was not called");
+  if (multi && peer && !finished) {
+    k_dot_peer_finish<<<1, 32, 0, c->stream>>>(w.result, sc, epi, k, nh, rh, ph, ah, gate, pd);
+    c->launches++;
+  } else if (multi && !peer) {
     CKN(g_nccl.AllGather(w.result, c->d_gather, 1, NCCL_FLOAT64, c->comm, c->stream));
     k_dot_allreduce_finish<<<1, 1, 0, c->stream>>>(c->d_gather, c->nranks, w.result, sc, epi, k, nh, rh, ph, ah, gate);
     c->launches++;
@@ -670,6 +881,18 @@ struct OpTimer {          // CUDA-event pairs per op class, resolved after the s
     return t * 1e-3;
   }
 };
+
+// a peer never delivered (bounded spins in peer.cuh): report instead of hanging
+static int peer_error(mfe_ctx *c)
+{
+  if (!c->peer.ok || !c->peer.d_err) return 0;
+  int e = 0;
+  if (cudaMemcpy(&e, c->peer.d_err, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return fail("peer_error: %s", cudaGetErrorString(cudaGetLastError()));
+  if (e == 0) return 0;
+  cudaMemset(c->peer.d_err, 0, 4);
+  return fail("NVLink peer %s timed out after %lld ms on rank %d (a neighbour rank died or fell behind)", e == 1 ? "halo exchange" : "dot all-reduce",
+              (long long)c->peer_timeout_ms, c->rank);
+}
 
 static int read_scalars(mfe_ctx *c, CgScalars *h)
 {
@@ -779,6 +1002,7 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
       rc = 2;
       break;
     }
+    if (h.status == CG_COMM_ERROR) break;
     if (h.status == CG_CONVERGED || h.stop_iter < k) break;
   }
   if (read_scalars(c, &h)) return 1;
@@ -803,6 +1027,7 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   if (pap_hist) memcpy(pap_hist, hh.data() + 2 * cap, cnt * 8);
   if (alpha_hist) memcpy(alpha_hist, hh.data() + 3 * cap, cnt * 8);
   CK(cudaGetLastError());
+  if (peer_error(c)) return 1;
   return rc;
 }
 
@@ -827,6 +1052,13 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
     c->dot_maps_warps = (int)value;
     return 0;
   }
+  if (!strcmp(name, "comm_mode")) {           // 1: NVLink peer stores (when every rank could open every mailbox), 0: NCCL
+    if (value != 0 && value != 1) return fail("mfe_set_option: comm_mode must be 0 (NCCL) or 1 (peer)");
+    c->comm_mode = (int)value;
+    return 0;
+  }
+  if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
+  if (!strcmp(name, "peer_timeout_ms")) { if (value < 1) return fail("mfe_set_option: peer_timeout_ms < 1"); c->peer_timeout_ms = value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
 
@@ -845,7 +1077,7 @@ extern "C" int mfe_matvec(mfe_ctx *c, double *x_host, double *y_host)
   if (c->nranks > 1) CK(cudaMemcpyAsync(x_host + c->nrows, c->d_tmp1 + c->nrows, (c->num_cols - c->nrows) * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
-  return 0;
+  return peer_error(c);
 }
 
 extern "C" int mfe_exchange_externals(mfe_ctx *c, double *x_host)
@@ -857,7 +1089,7 @@ extern "C" int mfe_exchange_externals(mfe_ctx *c, double *x_host)
   if (exchange(c, c->d_tmp1, nullptr, 0)) return 1;
   CK(cudaMemcpyAsync(x_host, c->d_tmp1, c->num_cols * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return peer_error(c);
 }
 
 extern "C" int mfe_waxpby(mfe_ctx *c, int64_t n, double alpha, const double *x_host, double beta, const double *y_host, double *w_host)
@@ -886,7 +1118,7 @@ extern "C" int mfe_dot(mfe_ctx *c, int64_t n, const double *x_host, const double
   CK(cudaMemcpyAsync(result, c->dot.w.result, 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
-  return 0;
+  return peer_error(c);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -908,6 +1140,7 @@ extern "C" int64_t mfe_get_map(const mfe_ctx *c, const char *name, int *out)
   else if (!strcmp(name, "neighbors")) v = &c->neighbors;
   else if (!strcmp(name, "recv_length")) v = &c->recv_length;
   else if (!strcmp(name, "send_length")) v = &c->send_length;
+  else if (!strcmp(name, "send_dst_offset")) v = &c->send_dst_offset;
   else return -1;
   if (out && !v->empty()) memcpy(out, v->data(), v->size() * sizeof(int));
   return (int64_t)v->size();
@@ -986,6 +1219,7 @@ extern "C" int mfe_import_csr(mfe_ctx *c, int64_t nrows, int64_t num_cols, const
   CK(cudaMemcpy(c->d_coefs, coefs, c->nnz * sizeof(double), cudaMemcpyHostToDevice));
   if (build_tile_base(c)) return 1;
   if (ensure_vectors(c, nrows, num_cols)) return 1;
+  if (c->nranks > 1 && classify_tiles(c)) return 1;
   CK(cudaStreamSynchronize(c->stream));
   c->has_structure = true; c->has_local = true;
   return 0;

@@ -10,6 +10,7 @@
 //              applies  [gap][dirty leaf][gap] ...  in order and runs the CG scalar epilogue
 #pragma once
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace mfe {
 
@@ -413,7 +414,7 @@ enum { WALK_THREADS = 512 };
 __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
                                                           DotWork w, CgScalars *sc, int epi, int k,
                                                           double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
-                                                          const CgScalars *gate)
+                                                          const CgScalars *gate, PeerDot pd)
 {
   if (cg_gate_closed(gate, k)) return;
   __shared__ int dirty[DOT_MAX_DIRTY];
@@ -486,11 +487,16 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
     }
   }
   if (tid == 0) {
-    *w.result = s;
     *w.dirty_count = 0;                         // ready for the next dot on this workspace
+    if (sc) sc->dot_local = s;
+  }
+  bool ok = true;
+  if (pd.nranks > 1) s = peer_dot_allreduce(pd, s, ok);     // rank-ordered global sum over NVLink peer memory
+  if (tid == 0) {
+    *w.result = s;
     if (sc) {
-      sc->dot_local = s;
-      if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist);
+      if (!ok) { sc->status = CG_COMM_ERROR; sc->stop_iter = -1; }
+      else if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist);
     }
   }
 }
@@ -513,6 +519,21 @@ __global__ void k_dot_tree_finish(const double *chunk_prefix, int nchunks, doubl
   const double s = chunk_prefix[nchunks];
   *result = s;
   if (sc) { sc->dot_local = s; if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist); }
+}
+// multi-rank over peer memory, for the dot modes that do not end in k_dot_walk: `result` holds the local dot
+__global__ void __launch_bounds__(32) k_dot_peer_finish(double *result, CgScalars *sc, int epi, int k, double *normr_hist, double *rtrans_hist,
+                                                        double *pap_hist, double *alpha_hist, const CgScalars *gate, PeerDot pd)
+{
+  if (cg_gate_closed(gate, k)) return;
+  bool ok = true;
+  const double g = peer_dot_allreduce(pd, threadIdx.x == 0 ? *result : 0.0, ok);
+  if (threadIdx.x == 0) {
+    *result = g;
+    if (sc) {
+      if (!ok) { sc->status = CG_COMM_ERROR; sc->stop_iter = -1; }
+      else if (epi != EPI_NONE) cg_epilogue(sc, epi, k, g, normr_hist, rtrans_hist, pap_hist, alpha_hist);
+    }
+  }
 }
 // multi-rank: rank-ordered sum of the gathered local dots ((r0+r1)+r2)+..., then the scalar bookkeeping
 __global__ void k_dot_allreduce_finish(const double *gathered, int nranks, double *result, CgScalars *sc, int epi, int k,

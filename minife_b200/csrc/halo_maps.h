@@ -15,6 +15,9 @@ struct ExtEntry { int64_t first; int grow; int owner; };
 
 struct LocalMaps {
   std::vector<int> external_index, external_local_index, elements_to_send, neighbors, recv_length, send_length;
+  // not a reference field: where neighbour i stores what I send it, as an offset into ITS external tail (its
+  // recv_length prefix up to me) -- lets the halo exchange store straight into the peer's memory over NVLink
+  std::vector<int> send_dst_offset;
   int64_t num_cols = 0;
 };
 
@@ -86,12 +89,15 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
   }
   // what each neighbour needs from me, in ITS external order (make_local_matrix.hpp:386-429)
   L.send_length.assign(L.neighbors.size(), 0);
+  L.send_dst_offset.assign(L.neighbors.size(), 0);
   std::vector<ExtEntry> pext; std::vector<int> pown; std::vector<std::vector<int>> pgrp;
   for (size_t i = 0; i < L.neighbors.size(); ++i) {
     externals_of(gm, L.neighbors[i], pext);
     group_externals(pext, pown, pgrp);
-    for (size_t g = 0; g < pown.size(); ++g) if (pown[g] == rank) {
+    int poff = 0;
+    for (size_t g = 0; g < pown.size(); poff += (int)pgrp[g].size(), ++g) if (pown[g] == rank) {
       L.send_length[i] = (int)pgrp[g].size();
+      L.send_dst_offset[i] = poff;
       for (int e : pgrp[g]) L.elements_to_send.push_back(pext[e].grow - first_row);
     }
   }

@@ -19,11 +19,11 @@ struct CgScalars {
   double one, zero, neg_one;
   double dot_local;      // result of the last local dot (before the rank-ordered sum)
   int stop_iter;         // kernels launched for iteration k do nothing when k > stop_iter
-  int status;            // 0 running, 1 converged, 2 breakdown (error), 3 paused: host must run breakdown()
+  int status;            // 0 running, 1 converged, 2 breakdown (error), 3 paused: host must run breakdown(), 4 peer lost
   int pause_iter;
   int max_iter;
 };
-enum { CG_RUNNING = 0, CG_CONVERGED = 1, CG_BREAKDOWN = 2, CG_PAUSED = 3 };
+enum { CG_RUNNING = 0, CG_CONVERGED = 1, CG_BREAKDOWN = 2, CG_PAUSED = 3, CG_COMM_ERROR = 4 };
 enum { EPI_NONE = 0, EPI_INIT_RR = 1, EPI_RR = 2, EPI_PAP = 3 };
 
 __device__ __forceinline__ bool cg_gate_closed(const CgScalars *g, int k) { return g != nullptr && k > g->stop_iter; }

@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(32 * G, 1)
 k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
          const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
          int64_t ntiles, int64_t nnz_padded, int zmask, double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
-         const CgScalars *gate, int k)
+         const CgScalars *gate, int k, const int *__restrict__ tile_list, int64_t nwork)
 {
+  // tile_list == nullptr: all tiles 0 .. ntiles-1 (nwork == ntiles).  Otherwise work item i is tile tile_list[i]
+  // (the interior or the boundary tiles of a rank, so that the halo exchange overlaps the interior pass).
   if (cg_gate_closed(gate, k)) return;
   constexpr int TR = MV_TILE_ROWS;
   constexpr int CAP = MatvecCfg::CAP;
@@ -63,7 +65,8 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   int *rcnt = reinterpret_cast<int *>(racc + 8);                                                  // [8] round arrivals
   uint64_t pol_stream = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  const int64_t stride = (int64_t)gridDim.x * G;      // this warp's tiles: (blockIdx.x + j * gridDim.x) * G + w
+  const int64_t stride = (int64_t)gridDim.x * G;      // this warp's work items: (blockIdx.x + j * gridDim.x) * G + w
+  auto tile_of = [&](int64_t i) -> int64_t { return tile_list ? (int64_t)tile_list[i] : i; };
 
   auto issue = [&](int64_t t, int s) {
     const int64_t a0 = tile_base[t] & ~3LL;
@@ -85,30 +88,33 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   if (threadIdx.x < 8) { racc[threadIdx.x] = 0.0; rcnt[threadIdx.x] = 0; }
   __syncthreads();
 
-  int64_t t = (int64_t)blockIdx.x * G + w;
+  int64_t wi = (int64_t)blockIdx.x * G + w;           // work item
   if (lane == 0)
-    for (int s = 0; s < S; ++s) { const int64_t ti = t + s * stride; if (ti < ntiles) issue(ti, s); }
+    for (int s = 0; s < S; ++s) { const int64_t ii = wi + s * stride; if (ii < nwork) issue(tile_of(ii), s); }
 
   uint32_t phase_bits = 0;            // expected mbarrier parity per stage (flips each time a stage completes)
   // software-pipelined row offsets: (o0,o1) of this lane's row in the NEXT tile are loaded one tile ahead
   uint32_t o0n = 0, o1n = 0; int64_t tb0n = 0, tb1n = 0;
-  if (t < ntiles) {
-    const int64_t r = t * TR + lane;
+  int64_t tnext = 0;
+  if (wi < nwork) {
+    tnext = tile_of(wi);
+    const int64_t r = tnext * TR + lane;
     if (r < nrows) { o0n = roff[r]; o1n = roff[r + 1]; }
-    tb0n = tile_base[t]; tb1n = tile_base[t + 1];
+    tb0n = tile_base[tnext]; tb1n = tile_base[tnext + 1];
   }
-  for (int64_t j = 0; t < ntiles; ++j, t += stride) {
+  for (int64_t j = 0; wi < nwork; ++j, wi += stride) {
     const int s = (int)(j % S);
     const uint32_t parity = (phase_bits >> s) & 1u;
+    const int64_t t = tnext;
     const int64_t r = t * TR + lane;
     const uint32_t o0 = o0n, o1 = o1n;
     const int64_t tb0 = tb0n, tb1 = tb1n;
-    const int64_t tn = t + stride;
-    if (tn < ntiles) {
-      const int64_t rn = tn * TR + lane;
+    if (wi + stride < nwork) {
+      tnext = tile_of(wi + stride);
+      const int64_t rn = tnext * TR + lane;
       o0n = 0; o1n = 0;
       if (rn < nrows) { o0n = roff[rn]; o1n = roff[rn + 1]; }
-      tb0n = tile_base[tn]; tb1n = tile_base[tn + 1];
+      tb0n = tile_base[tnext]; tb1n = tile_base[tnext + 1];
     }
     const int64_t a0 = tb0 & ~3LL;
     int64_t a1 = (tb1 + 3) & ~3LL;
@@ -173,10 +179,10 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     }
     __syncwarp();                     // every lane is done with stage s -> it can be refilled
     if (lane == 0) {
-      const int64_t t2 = t + (int64_t)S * stride;
-      if (t2 < ntiles) issue(t2, s);
+      const int64_t i2 = wi + (int64_t)S * stride;
+      if (i2 < nwork) issue(tile_of(i2), s);
       if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
-        if (G == 16) {
+        if (G == 16 && tile_list == nullptr) {
           // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
           // rounds; the warp that completes a round publishes it).  Prediction data: a lagging warp that lets a
           // slot be reused early can only blur a prediction.

@@ -185,6 +185,7 @@ long long hs_get_map(void *p, const char *name, int *out)
   else if (!strcmp(name, "neighbors")) v = &h->maps.neighbors;
   else if (!strcmp(name, "recv_length")) v = &h->maps.recv_length;
   else if (!strcmp(name, "send_length")) v = &h->maps.send_length;
+  else if (!strcmp(name, "send_dst_offset")) v = &h->maps.send_dst_offset;
   else return -1;
   if (out && !v->empty()) memcpy(out, v->data(), v->size() * sizeof(int));
   return (long long)v->size();

@@ -4,7 +4,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
         tests/mgpu_check.py [--sizes 8x8x8,20x30x40,64x64x64]
 
-Every rank builds its share with minife_b200 (NCCL halo exchange + rank-ordered dot allgather) and compares with the
+Every rank builds its share with minife_b200 (halo exchange + rank-ordered dot all-reduce, over NVLink peer stores with
+and without SpMV overlap and over NCCL) and compares with the
 CPU oracle run at the SAME number of ranks: CSR, index maps, exchange_externals, matvec, CG history and solution,
 all bit-exact.  Exit code 0 = all ranks agree."""
 import argparse
@@ -25,11 +26,14 @@ def main():
     from oracle_lib import Oracle, EPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="2x2x2,8x8x8,5x3x7,20x30x40,64x64x64")
+    ap.add_argument("--modes", default="peer+overlap,peer,nccl", help="communication modes to check: peer+overlap (NVLink peer stores, "
+                    "interior SpMV overlapped), peer (no overlap), nccl (send/recv + allgather)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = []
+    oracles = {}
 
     def bits(a):
         return np.ascontiguousarray(a, np.float64).view(np.int64)
@@ -39,7 +43,7 @@ def main():
             failures.append(what)
             print("[rank %d] MISMATCH: %s" % (rank, what), flush=True)
 
-    for size in args.sizes.split(","):
+    for size, mode in [(s_, m_) for s_ in args.sizes.split(",") for m_ in args.modes.split(",")]:
         n = tuple(int(v) for v in size.split("x"))
         if min(n) * 1 < 1 or (n[0] * n[1] * n[2]) < world:
             continue
@@ -53,13 +57,20 @@ def main():
             idt.copy_(torch.frombuffer(bytearray(mf.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
         mesh.comm_init(bytes(idt.cpu().numpy().tobytes()))
+        mesh.set_option("comm_mode", 0 if mode == "nccl" else 1)
+        mesh.set_option("overlap", 1 if mode == "peer+overlap" else 0)
+        size = "%s[%s]" % (size, mode)
         A = mf.CSRMatrix()
         mf.generate_matrix_structure(mesh, A)
         b = mf.Vector(int(A.rows[0]), A.num_rows()); x = mf.Vector(int(A.rows[0]), A.num_rows())
         mf.assemble_FE_data(mesh, A, b)
         mf.impose_dirichlet(0.0, A, b, bc_rows=0); mf.impose_dirichlet(1.0, A, b, bc_rows=1)
         mf.make_local_matrix(A)
-        o = Oracle(*n, world).setup()
+        if n not in oracles:
+            oracles.clear()
+            oracles[n] = Oracle(*n, world).setup()
+            oracles[n]._cg = oracles[n].cg_solve(200, EPS)
+        o = oracles[n]
         rows, ro, cols, coefs = o.csr(rank)
         check(np.array_equal(A.row_offsets, ro) and np.array_equal(A.packed_cols, cols), "%s CSR structure" % size)
         check(np.array_equal(bits(A.packed_coefs), bits(coefs)) and np.array_equal(bits(b.coefs), bits(o.b(rank))), "%s A/b values" % size)
@@ -81,7 +92,7 @@ def main():
         xo = xv.copy(); xo[A.num_rows():] = want_tail
         check(np.array_equal(bits(y), bits(o.matvec(xo, rank))), "%s matvec" % size)
         # free-running CG against the oracle at np = world
-        want = o.cg_solve(200, EPS)
+        want = o._cg
         iters, normr, times, h = mf.cg_solve(A, b, x, mf.matvec_std(), 200, EPS, history=True)
         check(iters == want["num_iters"], "%s iterations %d vs %d" % (size, iters, want["num_iters"]))
         k = min(iters, want["num_iters"])

@@ -61,6 +61,22 @@ def _worker(rank, world, port, n, so, q):
         ext = o.get_map("external_index", rank); loc = o.get_map("external_local_index", rank)
         want = np.zeros(ncols - nrows); want[loc - nrows] = np.cos(0.1 * ext.astype(np.float64)) + 2.0
         ok = np.array_equal(x[nrows:].view(np.int64), want.view(np.int64))
+        # the NVLink peer-store exchange (peer.cuh): the SENDER chooses where its values land in the receiver's
+        # external tail (send_dst_offset, derived from the box table alone) -- must give the same tail
+        sdo = gm("send_dst_offset")
+        tail = np.zeros(ncols - nrows)
+        reqs, so_, inbox = [], 0, []
+        for i, p in enumerate(nb):
+            buf = torch.zeros(1 + int(rl[i]), dtype=torch.float64); inbox.append(buf)
+            reqs.append(dist.irecv(buf, src=int(p)))
+        for i, p in enumerate(nb):
+            seg = np.concatenate([[float(sdo[i])], x[ets[so_:so_ + int(sl[i])]]]); so_ += int(sl[i])
+            reqs.append(dist.isend(torch.from_numpy(seg.copy()), dst=int(p)))
+        for r in reqs:
+            r.wait()
+        for buf in inbox:
+            off = int(buf[0]); tail[off:off + len(buf) - 1] = buf[1:].numpy()
+        ok = ok and np.array_equal(tail.view(np.int64), want.view(np.int64))
         # dot: local serial sum, all-gather, sum in rank order (Vector_functions.hpp:218-222 through the MPI shim)
         local = torch.tensor([Oracle.dot(x[:nrows], x[:nrows])], dtype=torch.float64)
         parts = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
