@@ -164,11 +164,11 @@ def reference_arm(args, rank):
         last = r
     gf = float(np.mean([v["cg_mflops"] for v in vals])) / 1e3
     ms = float(np.mean([v["cg_time"] for v in vals])) * 1e3
-    dims = weak_dims(args.nx, args.gpus)
+    dims = [args.nx] * 3 if args.strong else weak_dims(args.nx, args.gpus)
     desc = "reference %s build, nx=ny=nz=%d (bounded sample of the %dx%dx%d workload), %d host threads, full 200-iteration cg_solve per step" % (
         "OpenMP (openmp/src, unmodified)" if last["kind"] == "reference" else "C port", sample, dims[0], dims[1], dims[2], last["cores"])
     line = {"impl": "reference", "metric": "cg_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "miniFE %dx%dx%d hex8 Poisson, 200-iteration unpreconditioned CG" % tuple(dims), "sample": desc},
             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": last["cores"], "kind": last["kind"], "sample": desc},
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -182,7 +182,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--nx", type=int, default=256, help="elements per GPU per dimension")
+    ap.add_argument("--nx", type=int, default=256, help="elements per GPU per dimension (weak scaling), or of the whole mesh with --strong")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the global mesh is nx^3 whatever --gpus is (BASELINE.json configs[2]: --nx 400 --strong)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-nx", type=int, default=128, help="size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -212,7 +213,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    dims = weak_dims(args.nx, world)
+    dims = [args.nx] * 3 if args.strong else weak_dims(args.nx, world)
     gbox = mf.Box([0, dims[0], 0, dims[1], 0, dims[2]])
     boxes = mf.box_partition(0, world, 2, gbox)
     mesh = mf.simple_mesh_description(gbox, boxes[rank], rank=rank, nranks=world, all_boxes=boxes, device=local_rank)
@@ -340,12 +341,13 @@ def main():
                        r.get("assembly_time") or float("nan"), r.get("struct_time") or float("nan"))}
         line = {
             "metric": "cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "miniFE %dx%dx%d hex8 Poisson (%d^3 elements per GPU), assembled on device, 200-iteration unpreconditioned CG" % (dims[0], dims[1], dims[2], args.nx),
+            "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "miniFE %dx%dx%d hex8 Poisson (%s), assembled on device, 200-iteration unpreconditioned CG" % (
+                           dims[0], dims[1], dims[2], "strong scaling: fixed global mesh" if args.strong else "%d^3 elements per GPU" % args.nx),
                        "rows": nrows_g, "nnz": nnz_g, "cg_iterations": iters, "final_resid": normr, "parallelism": "box_partition x%d, 1 rank per GPU" % world,
                        "comm": (None if world == 1 else ("NCCL send/recv + allgather" if args.comm == "nccl" else
                                 "NVLink peer stores (halo + dot all-reduce)%s" % ("" if args.no_overlap else ", halo overlapped with the interior SpMV tiles"))),
-                       "l2": "inputs larger than L2 (7.4 GB per iteration vs 126 MB)", "dot": ["exact (order-reproducing)", "serial", "tree"][args.dot_mode],
+                       "l2": "inputs larger than L2 (%.1f GB per iteration per GPU vs 126 MB)" % ((12.0 * nnz + 116.0 * nrows) / 1e9), "dot": ["exact (order-reproducing)", "serial", "tree"][args.dot_mode],
                        "flop_model": "ref/src/driver.hpp:322-341"},
             "hbm_gbs": hbm_gbs, "hbm_gbs_per_gpu": hbm_gbs / world, "pct_of_8TBs_per_gpu": 100.0 * hbm_gbs / world / 8000.0,
             "ms_per_cg_iteration": t_step * 1e3 / max(iters, 1), "cg_times": cg_times,

@@ -70,8 +70,18 @@ int mfe_make_local_matrix(mfe_ctx *ctx, int64_t *num_cols);
 int mfe_cg_solve(mfe_ctx *ctx, double *x_host, int max_iter, double tolerance, int *num_iters, double *normr,
                  double cg_times[MFE_NUM_TIMERS], double *normr_hist, double *rtrans_hist, double *pap_hist,
                  double *alpha_hist);
+/* ref/fem/verify_solution.hpp:55-174 (+ analytic_soln.hpp:69-118) on the device-resident x left by mfe_cg_solve
+ * (or mfe_import_vector "x"): compares x with the 301x301-term analytic series at the nodes within 0.05 of the
+ * cube centre (verify_whole_domain = 0, driver.hpp:296) or at every owned node.  *return_code = the reference's
+ * return value (1 when the GLOBAL max error exceeds tolerance); local_info[6] = this rank's {max err, computed,
+ * analytic, x, y, z} (err_info, verify_solution.hpp:47-53); global_max_err = max over ranks. */
+int mfe_verify_solution(mfe_ctx *ctx, double tolerance, int verify_whole_domain, int *return_code, double *global_max_err,
+                        double local_info[6]);
 int mfe_set_dot_mode(mfe_ctx *ctx, int mode);
-/* tuning knobs: "matvec_config" = index into the SpMV (rows-per-tile, groups, stages) table */
+/* knobs: "matvec_config" = index into the SpMV (warps, stages, gather batches) table; "comm_mode" = 1 NVLink peer
+ * stores for halo + dot all-reduce (default when every rank can map every other rank's mailbox through CUDA IPC),
+ * 0 NCCL send/recv + allgather; "overlap" = 1 run the SpMV tiles that need no halo while the halo is in flight
+ * (peer mode); "peer_timeout_ms" = bound of every peer spin (default 30000); "dot_maps_warps" = 0 | 16 | 24 */
 int mfe_set_option(mfe_ctx *ctx, const char *name, int64_t value);
 /* CUDA events inside mfe_cg_solve: 1 = around every op class, filling cg_times[WAXPY,DOT,MATVEC] (default);
  * 2 = around the SpMV only (two events per iteration: cg_times[MATVEC]); 0 = none (only TOTAL) */

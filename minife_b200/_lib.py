@@ -36,6 +36,7 @@ SIGNATURES = {
     "mfe_impose_dirichlet": (C.c_int, [_vp, C.c_double, C.c_int]),
     "mfe_make_local_matrix": (C.c_int, [_vp, _pi64]),
     "mfe_cg_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp]),
+    "mfe_verify_solution": (C.c_int, [_vp, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp]),
     "mfe_set_dot_mode": (C.c_int, [_vp, C.c_int]),
     "mfe_set_op_timing": (C.c_int, [_vp, C.c_int]),
     "mfe_set_option": (C.c_int, [_vp, C.c_char_p, _i64]),

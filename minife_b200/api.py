@@ -274,3 +274,18 @@ def cg_solve(A, b, x, matvec_op=None, max_iter=200, tolerance=float(np.finfo(np.
         k = it.value
         return it.value, nr.value, times, dict(rc=rc, **{kk: v[:k + 1] for kk, v in hist.items()})
     return it.value, nr.value, times
+
+
+def verify_solution(mesh, x=None, tolerance=0.06, verify_whole_domain=False, info=False):
+    """ref/fem/verify_solution.hpp:55-174 on the DEVICE-resident solution (the x left by cg_solve; pass a Vector /
+    array to upload a different one first).  Returns the reference's return code (0 = within tolerance); with
+    ``info=True`` also ``(global_max_err, dict(err, computed, analytic, coords))`` of this rank's worst node."""
+    L = lib()
+    if x is not None:
+        xs = x.coefs if isinstance(x, Vector) else x
+        check(L.mfe_import_vector(mesh._h, b"x", np.ascontiguousarray(xs, np.float64)), "import x")
+    rc, gmax, loc = C.c_int(0), C.c_double(0), np.zeros(6)
+    check(L.mfe_verify_solution(mesh._h, float(tolerance), int(bool(verify_whole_domain)), C.byref(rc), C.byref(gmax), _vp(loc)), "verify_solution")
+    if info:
+        return rc.value, gmax.value, dict(err=loc[0], computed=loc[1], analytic=loc[2], coords=tuple(loc[3:6]))
+    return rc.value

@@ -16,6 +16,7 @@
 #include "spmv.cuh"
 #include "dot_kernels.cuh"
 #include "halo_maps.h"
+#include "verify.cuh"
 
 using namespace mfe;
 
@@ -146,7 +147,8 @@ struct mfe_ctx {
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
   int64_t peer_timeout_ms = 30000;
   std::vector<int> send_dst_offset;
-  int *d_tiles_interior = nullptr, *d_tiles_boundary = nullptr;   // SpMV tiles without / with external columns
+  int *d_tiles_boundary = nullptr;          // SpMV tiles that reference external columns (second pass, after the halo)
+  int64_t *d_tile_base_flagged = nullptr;   // tile_base with bit 62 set on those tiles (first pass skips them)
   int64_t n_interior = 0, n_boundary = 0;
 
   // phase timings (ms)
@@ -293,7 +295,7 @@ extern "C" void mfe_destroy(mfe_ctx *c)
   if (c->stream) cudaStreamSynchronize(c->stream);
   peer_teardown(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  free_dev(c->d_tiles_interior); free_dev(c->d_tiles_boundary);
+  free_dev(c->d_tile_base_flagged); free_dev(c->d_tiles_boundary);
   free_matrix(c); free_vectors(c);
   free_dev(c->d_boxes); free_dev(c->d_sc); free_dev(c->d_hist); free_dev(c->d_gather);
   free_dev(c->d_elements_to_send); free_dev(c->d_send_buf);
@@ -578,23 +580,21 @@ extern "C" int mfe_impose_dirichlet(mfe_ctx *c, double val, int which)
 // SparseMatrix_functions.hpp:624-675, without re-ordering the matrix: whole rows stay intact and bit-exact).
 static int classify_tiles(mfe_ctx *c)
 {
-  free_dev(c->d_tiles_interior); free_dev(c->d_tiles_boundary);
-  c->d_tiles_interior = c->d_tiles_boundary = nullptr; c->n_interior = c->n_boundary = 0;
+  free_dev(c->d_tile_base_flagged); free_dev(c->d_tiles_boundary);
+  c->d_tile_base_flagged = nullptr; c->d_tiles_boundary = nullptr; c->n_interior = c->n_boundary = 0;
   if (c->ntiles <= 0 || c->ntiles > 0x7fffffffLL) return 0;
   unsigned char *d_flag = nullptr;
-  if (dev_alloc(&d_flag, c->ntiles)) return 1;
-  k_classify_tiles<<<grid_for(c->ntiles * 32, 256), 256, 0, c->stream>>>(c->d_cols, c->d_tile_base, c->ntiles, (int)c->nrows, d_flag);
+  if (dev_alloc(&d_flag, c->ntiles) || dev_alloc(&c->d_tile_base_flagged, c->ntiles + 2)) return 1;
+  k_classify_tiles<<<grid_for((c->ntiles + 1) * 32, 256), 256, 0, c->stream>>>(c->d_cols, c->d_tile_base, c->ntiles, (int)c->nrows, d_flag, c->d_tile_base_flagged);
   c->launches++;
   std::vector<unsigned char> flag(c->ntiles);
   CK(cudaMemcpyAsync(flag.data(), d_flag, c->ntiles, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   cudaFree(d_flag);
-  std::vector<int> in, bd;
-  in.reserve(c->ntiles);
-  for (int64_t t = 0; t < c->ntiles; ++t) (flag[t] ? bd : in).push_back((int)t);
-  c->n_interior = (int64_t)in.size(); c->n_boundary = (int64_t)bd.size();
-  if (dev_alloc(&c->d_tiles_interior, c->n_interior + 1) || dev_alloc(&c->d_tiles_boundary, c->n_boundary + 1)) return 1;
-  if (!in.empty()) CK(cudaMemcpyAsync(c->d_tiles_interior, in.data(), sizeof(int) * in.size(), cudaMemcpyHostToDevice, c->stream));
+  std::vector<int> bd;
+  for (int64_t t = 0; t < c->ntiles; ++t) if (flag[t]) bd.push_back((int)t);
+  c->n_boundary = (int64_t)bd.size(); c->n_interior = c->ntiles - c->n_boundary;
+  if (dev_alloc(&c->d_tiles_boundary, c->n_boundary + 1)) return 1;
   if (!bd.empty()) CK(cudaMemcpyAsync(c->d_tiles_boundary, bd.data(), sizeof(int) * bd.size(), cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
@@ -661,7 +661,7 @@ static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {12,
 enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
 
 template <int G, int S, int H>
-static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork)
+static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
 {
   static bool attr_set[64] = { false };
   const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 64;
@@ -673,26 +673,26 @@ static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_s
   if (!tile_list) nwork = c->ntiles;
   if (nwork <= 0) return 0;
   const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (nwork + G - 1) / G));
-  kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, 0,
+  kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, tile_base ? tile_base : c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, 0,
                                           with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork);
   c->launches++;
   return 0;
 }
 
 static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k,
-                               const int *tile_list = nullptr, int64_t nwork = 0)
+                               const int *tile_list = nullptr, int64_t nwork = 0, const int64_t *tile_base = nullptr)
 {
   switch (c->mv_cfg) {
-    case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 3: return launch_matvec_cfg<12, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 4: return launch_matvec_cfg<14, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 5: return launch_matvec_cfg<18, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 6: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 7: return launch_matvec_cfg<21, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 8: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork);
-    case 9: return launch_matvec_cfg<20, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork);
+    case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 3: return launch_matvec_cfg<12, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 4: return launch_matvec_cfg<14, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 5: return launch_matvec_cfg<18, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 6: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 7: return launch_matvec_cfg<21, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 8: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 9: return launch_matvec_cfg<20, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
   }
   return fail("bad matvec configuration %d", c->mv_cfg);
 }
@@ -768,7 +768,7 @@ static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const
 {
   if (exchange_begin(c, x, gate, k)) return 1;
   if (use_peer(c) && c->overlap && c->n_interior > 0 && c->n_boundary > 0) {
-    if (launch_matvec_local(c, x, y, with_sums, gate, k, c->d_tiles_interior, c->n_interior)) return 1;   // needs no halo
+    if (launch_matvec_local(c, x, y, with_sums, gate, k, nullptr, 0, c->d_tile_base_flagged)) return 1;   // skips the tiles that need the halo
     if (exchange_end(c, x, gate, k)) return 1;
     return launch_matvec_local(c, x, y, with_sums, gate, k, c->d_tiles_boundary, c->n_boundary);
   }
@@ -1029,6 +1029,71 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   CK(cudaGetLastError());
   if (peer_error(c)) return 1;
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// verify_solution: ref/fem/verify_solution.hpp:55-174 on the device-resident x
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mfe_verify_solution(mfe_ctx *c, double tolerance, int verify_whole_domain, int *return_code, double *global_max_err, double local_info[6])
+{
+  if (!c || !c->has_structure || !c->d_x) return fail("mfe_verify_solution: no solution vector (run mfe_generate_matrix_structure / mfe_cg_solve first)");
+  CK(cudaSetDevice(c->device));
+  const MeshDesc &m = c->m;
+  // verified nodes: the condition is separable per axis (verify_solution.hpp:90-95), so they are a product of index sets
+  std::vector<int> v[3];
+  const int gn[3] = { m.gnx, m.gny, m.gnz };
+  for (int a = 0; a < 3; ++a) {
+    const int div = gn[a] > 1 ? gn[a] - 1 : 1;
+    for (int i = m.nb[2 * a]; i < m.nb[2 * a + 1]; ++i) {
+      const double coord = (1.0 * i) / div;
+      if (verify_whole_domain || std::abs(coord - 0.5) < 0.05) v[a].push_back(i);
+    }
+  }
+  const int64_t npts = (int64_t)v[0].size() * (int64_t)v[1].size() * (int64_t)v[2].size();
+  double info[6] = { 0, 0, 0, 0, 0, 0 };      // err, computed, analytic, x, y, z  (err_info, verify_solution.hpp:47-53)
+  if (npts > 0x7fffffffLL) return fail("mfe_verify_solution: %lld points", (long long)npts);
+  if (npts > 0) {
+    int *d_v[3] = { nullptr, nullptr, nullptr };
+    double *d_l = nullptr, *d_s = nullptr, *d_err = nullptr, *d_an = nullptr;
+    for (int a = 0; a < 3; ++a) {
+      if (dev_alloc(&d_v[a], (int64_t)v[a].size())) return 1;
+      CK(cudaMemcpyAsync(d_v[a], v[a].data(), sizeof(int) * v[a].size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (dev_alloc(&d_l, VERIFY_NT * VERIFY_NT) || dev_alloc(&d_s, VERIFY_NT * VERIFY_NT) || dev_alloc(&d_err, npts) || dev_alloc(&d_an, npts)) return 1;
+    k_verify_tables<<<grid_for(VERIFY_NT * VERIFY_NT, 256), 256, 0, c->stream>>>(d_l, d_s);
+    VerifyAxes va; for (int a = 0; a < 3; ++a) va.n[a] = (int)v[a].size();
+    k_verify<<<(unsigned)npts, VERIFY_THREADS, 0, c->stream>>>(m, va, d_v[0], d_v[1], d_v[2], c->d_x, d_l, d_s, d_err, d_an);
+    c->launches += 2;
+    std::vector<double> err(npts);
+    CK(cudaMemcpyAsync(err.data(), d_err, 8 * npts, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    int64_t best = -1;                            // first strictly larger error in row order (verify_solution.hpp:139-146)
+    for (int64_t i = 0; i < npts; ++i) if (err[i] > info[0]) { info[0] = err[i]; best = i; }
+    if (best >= 0) {
+      const int ix = v[0][best % v[0].size()], iy = v[1][(best / v[0].size()) % v[1].size()], iz = v[2][best / (v[0].size() * v[1].size())];
+      const int64_t lr = (int64_t)(ix - m.nb[0]) + (int64_t)m.lnx * ((iy - m.nb[2]) + (int64_t)m.lny * (iz - m.nb[4]));
+      CK(cudaMemcpy(&info[1], c->d_x + lr, 8, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(&info[2], d_an + best, 8, cudaMemcpyDeviceToHost));
+      info[3] = (1.0 * ix) / (gn[0] > 1 ? gn[0] - 1 : 1); info[4] = (1.0 * iy) / (gn[1] > 1 ? gn[1] - 1 : 1); info[5] = (1.0 * iz) / (gn[2] > 1 ? gn[2] - 1 : 1);
+    }
+    for (int a = 0; a < 3; ++a) cudaFree(d_v[a]);
+    cudaFree(d_l); cudaFree(d_s); cudaFree(d_err); cudaFree(d_an);
+  }
+  double gmax = info[0];
+  if (c->nranks > 1) {                            // MPI_Allreduce(MAX), verify_solution.hpp:148-154
+    if (!c->comm) return fail("mfe_verify_solution: nranks > 1 but mfe_comm_init was not called");
+    std::vector<double> all(c->nranks);
+    CK(cudaMemcpyAsync(c->d_tmp1, &info[0], 8, cudaMemcpyHostToDevice, c->stream));
+    CKN(g_nccl.AllGather(c->d_tmp1, c->d_gather, 1, NCCL_FLOAT64, c->comm, c->stream));
+    CK(cudaMemcpyAsync(all.data(), c->d_gather, 8 * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (double e : all) gmax = std::max(gmax, e);
+  }
+  if (local_info) memcpy(local_info, info, sizeof info);
+  if (global_max_err) *global_max_err = gmax;
+  if (return_code) *return_code = gmax > tolerance ? 1 : 0;
+  CK(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int mfe_set_dot_mode(mfe_ctx *c, int mode)

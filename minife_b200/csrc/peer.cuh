@@ -162,17 +162,19 @@ __device__ __forceinline__ double peer_dot_allreduce(const PeerDot &pd, double l
   return g;
 }
 
-// tiles (MV_TILE_ROWS consecutive rows) that reference an external column (col >= nrows): one warp per tile
+// tiles (MV_TILE_ROWS consecutive rows) that reference an external column (col >= nrows): one warp per tile.
+// Also writes the flagged copy of tile_base the interior SpMV pass uses (bit 62 = skip this tile).
 __global__ void k_classify_tiles(const int *__restrict__ cols, const int64_t *__restrict__ tile_base, int64_t ntiles, int nrows,
-                                 unsigned char *__restrict__ is_boundary)
+                                 unsigned char *__restrict__ is_boundary, int64_t *__restrict__ tile_base_flagged)
 {
   const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (t >= ntiles) return;
+  if (t > ntiles) return;
+  if (t == ntiles) { if (lane == 0) tile_base_flagged[t] = tile_base[t]; return; }
   bool ext = false;
   for (int64_t i = tile_base[t] + lane; i < tile_base[t + 1]; i += 32) ext = ext || cols[i] >= nrows;
   const unsigned any = __ballot_sync(0xffffffffu, ext);
-  if (lane == 0) is_boundary[t] = any != 0;
+  if (lane == 0) { is_boundary[t] = any != 0; tile_base_flagged[t] = tile_base[t] | (any ? (1LL << 62) : 0LL); }
 }
 
 }  // namespace mfe

@@ -22,6 +22,7 @@
 namespace mfe {
 
 enum { MV_TILE_ROWS = 32 };
+#define MV_SKIP_BIT (1LL << 62)
 struct MatvecCfg {
   static constexpr int CAP = MV_TILE_ROWS * 27 + 8;                // nnz capacity of one stage
   static constexpr int SLOT_BYTES = ((CAP * 12 + 127) / 128) * 128;
@@ -50,7 +51,9 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
          const CgScalars *gate, int k, const int *__restrict__ tile_list, int64_t nwork)
 {
   // tile_list == nullptr: all tiles 0 .. ntiles-1 (nwork == ntiles).  Otherwise work item i is tile tile_list[i]
-  // (the interior or the boundary tiles of a rank, so that the halo exchange overlaps the interior pass).
+  // (the boundary tiles of a rank, after the halo arrived).  The interior pass that overlaps the halo exchange runs
+  // over all tiles in natural order with a FLAGGED copy of tile_base: bit 62 of tile_base[t] set = skip tile t
+  // (it references external columns), so the flag costs no extra load on the TMA issue path.
   if (cg_gate_closed(gate, k)) return;
   constexpr int TR = MV_TILE_ROWS;
   constexpr int CAP = MatvecCfg::CAP;
@@ -69,8 +72,10 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   auto tile_of = [&](int64_t i) -> int64_t { return tile_list ? (int64_t)tile_list[i] : i; };
 
   auto issue = [&](int64_t t, int s) {
-    const int64_t a0 = tile_base[t] & ~3LL;
-    int64_t a1 = (tile_base[t + 1] + 3) & ~3LL;
+    const int64_t b0 = tile_base[t];
+    if (b0 & MV_SKIP_BIT) return;                       // skipped in this pass: nothing to stage
+    const int64_t a0 = b0 & ~3LL;
+    int64_t a1 = ((tile_base[t + 1] & ~MV_SKIP_BIT) + 3) & ~3LL;
     if (a1 > nnz_padded) a1 = nnz_padded;
     const int64_t n = a1 - a0;
     if (n <= 0 || n > CAP) return;                      // oversized tile: consumers read global memory directly
@@ -108,7 +113,8 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     const int64_t t = tnext;
     const int64_t r = t * TR + lane;
     const uint32_t o0 = o0n, o1 = o1n;
-    const int64_t tb0 = tb0n, tb1 = tb1n;
+    const bool skipped = (tb0n & MV_SKIP_BIT) != 0;
+    const int64_t tb0 = tb0n & ~MV_SKIP_BIT, tb1 = tb1n & ~MV_SKIP_BIT;
     if (wi + stride < nwork) {
       tnext = tile_of(wi + stride);
       const int64_t rn = tnext * TR + lane;
@@ -120,8 +126,8 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     int64_t a1 = (tb1 + 3) & ~3LL;
     if (a1 > nnz_padded) a1 = nnz_padded;
     const int64_t ntile = a1 - a0;
-    const bool staged = ntile > 0 && ntile <= CAP;
-    const bool live = r < nrows;
+    const bool staged = !skipped && ntile > 0 && ntile <= CAP;
+    const bool live = !skipped && r < nrows;
     const int len = live ? (int)(o1 - o0) : 0;
     const bool full = staged && __all_sync(0xffffffffu, len == U);
 

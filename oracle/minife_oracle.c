@@ -661,3 +661,67 @@ long long mfo_get_map(mfo_world *w, int p, const char *name, int *out)
   if (out && src && n > 0) memcpy(out, src, sizeof(int) * n);
   return n;
 }
+
+/* ---- ref/fem/analytic_soln.hpp:56-118 ------------------------------------------------------------ */
+static const double AS_PI = 3.141592653589793238462;
+static double as_fcn_l(int p, int q)
+{
+  const double PI_SQR = AS_PI * AS_PI;
+  return sqrt((2 * p + 1) * (2 * p + 1) * PI_SQR + (2 * q + 1) * (2 * q + 1) * PI_SQR);     /* :71-74 */
+}
+static double as_fcn(int n, double u) { return (2 * n + 1) * AS_PI * u; }                     /* :76-79 */
+static double as_soln(double x, double y, double z, int max_p, int max_q)                     /* :81-116 */
+{
+  const double PI_SQR = AS_PI * AS_PI, term0 = 16.0 / PI_SQR;
+  double sum = 0;
+  int p, q;
+  for (p = 0; p <= max_p; ++p) {
+    const double p21y = as_fcn(p, y);
+    const double sin_py = sin(p21y) / (2 * p + 1);
+    for (q = 0; q <= max_q; ++q) {
+      const double q21z = as_fcn(q, z);
+      const double sin_qz = sin(q21z) / (2 * q + 1);
+      const double l = as_fcn_l(p, q);
+      const double sinh1 = sinh(l * x);
+      const double sinh2 = sinh(l);
+      const double tmp = (sinh1 * sin_py) * (sin_qz / sinh2);
+      if (tmp == tmp) sum += tmp;
+      else break;
+    }
+  }
+  return term0 * sum;
+}
+
+/* ---- ref/fem/verify_solution.hpp:55-174 ----------------------------------------------------------
+ * Verifies the x left by mfo_cg_solve (or mfo_set_x).  info6 (may be NULL) = {max err, computed, analytic,
+ * x, y, z} of the rank holding the global maximum (lowest such rank).  Returns the reference's return code. */
+int mfo_verify_solution(mfo_world *w, double tolerance, int verify_whole_domain, double *global_max_err, double *info6)
+{
+  const int num_terms = 300;
+  double gmax = 0.0, best[6] = { 0, 0, 0, 0, 0, 0 };
+  int p;
+  for (p = 0; p < w->np; ++p) {
+    const mfo_rank *R = &w->r[p];
+    double loc[6] = { 0, 0, 0, 0, 0, 0 };
+    int roffset = 0, ix, iy, iz;
+    const int xdiv = w->gnx > 1 ? w->gnx - 1 : 1, ydiv = w->gny > 1 ? w->gny - 1 : 1, zdiv = w->gnz > 1 ? w->gnz - 1 : 1;
+    for (iz = R->nbox[4]; iz < R->nbox[5]; ++iz)
+      for (iy = R->nbox[2]; iy < R->nbox[3]; ++iy)
+        for (ix = R->nbox[0]; ix < R->nbox[1]; ++ix, ++roffset) {
+          /* get_coords, ref/utils/box_utils.hpp:68-82, of id = get_id(ix,iy,iz) */
+          const double z = (1.0 * iz) / zdiv, y = 1.0 * iy / ydiv, x = 1.0 * ix / xdiv;
+          double analytic, err;
+          if (!(verify_whole_domain || (fabs(x - 0.5) < 0.05 && fabs(y - 0.5) < 0.05 && fabs(z - 0.5) < 0.05))) continue;
+          if (x == 1.0) analytic = 1;
+          else if (x == 0.0 || y == 0.0 || z == 0.0) analytic = 0;
+          else if (y == 1.0 || z == 1.0) analytic = 0;
+          else analytic = as_soln(x, y, z, num_terms, num_terms);
+          err = fabs(analytic - R->x[roffset]);
+          if (err > loc[0]) { loc[0] = err; loc[1] = R->x[roffset]; loc[2] = analytic; loc[3] = x; loc[4] = y; loc[5] = z; }
+        }
+    if (loc[0] > gmax) { gmax = loc[0]; memcpy(best, loc, sizeof best); }
+  }
+  if (global_max_err) *global_max_err = gmax;
+  if (info6) memcpy(info6, best, sizeof best);
+  return gmax > tolerance ? 1 : 0;
+}

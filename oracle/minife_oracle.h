@@ -45,6 +45,10 @@ void mfo_make_local_matrix(mfo_world *w);             /* make_local_matrix.hpp:4
 int  mfo_cg_solve(mfo_world *w, int max_iter, double tol, int *num_iters, double *normr,
                   double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist);
 
+/* ref/fem/verify_solution.hpp:55-174 + analytic_soln.hpp:56-118 on the x of every rank (as left by mfo_cg_solve or
+ * mfo_set_x).  Returns the reference's return code; info6 = {max err, computed, analytic, x, y, z}. */
+int  mfo_verify_solution(mfo_world *w, double tolerance, int verify_whole_domain, double *global_max_err, double *info6);
+
 /* per-rank queries */
 long long mfo_nrows(mfo_world *w, int rank);
 long long mfo_nnz(mfo_world *w, int rank);

@@ -98,6 +98,11 @@ def main():
         k = min(iters, want["num_iters"])
         check(np.array_equal(bits(h["normr"][:k + 1]), bits(want["normr"][:k + 1])), "%s residual history" % size)
         check(np.array_equal(bits(x.coefs), bits(o.x(rank))), "%s solution" % size)
+        # verify_solution on the device-resident x, MAX over ranks (ref/fem/verify_solution.hpp:148-154)
+        whole = n[0] * n[1] * n[2] <= 20 * 30 * 40
+        vrc, vmax, _ = mf.verify_solution(mesh, None, 0.06, whole, info=True)
+        wrc, wmax, _ = o.verify_solution(0.06, whole, info=True)
+        check(vrc == wrc and abs(vmax - wmax) <= 1e-12 * max(wmax, 1e-30) + 1e-15, "%s verify_solution %r vs %r" % (size, (vrc, vmax), (wrc, wmax)))
         if rank == 0:
             rel = np.abs(h["normr"][:k + 1] - want["normr"][:k + 1]) / np.maximum(want["normr"][:k + 1], 1e-300)
             print("size %s np=%d: iters %d (oracle %d), final resid %.6g, max rel diff of history %.3g" % (size, world, iters, want["num_iters"], normr, rel.max()), flush=True)

@@ -80,6 +80,7 @@ class Oracle:
             L.mfo_dot.restype = C.c_double
             L.mfo_dot.argtypes = [C.c_longlong, _f64p, _f64p]
             L.mfo_cg_solve.argtypes = [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double)] + [C.c_void_p] * 4
+            L.mfo_verify_solution.argtypes = [C.c_void_p, C.c_double, C.c_int, C.POINTER(C.c_double), _f64p]
             L.mfo_box_partition.argtypes = [C.c_int] * 4 + [_i32p]
             L.mfo_gradient_values.argtypes = [_f64p]
             L.mfo_element.argtypes = [C.c_int] * 4 + [_i32p, _f64p, _f64p, _f64p]
@@ -132,6 +133,11 @@ class Oracle:
                                  _ptr(hist["rtrans"]), _ptr(hist["pap"]), _ptr(hist["alpha"]))
         k = it.value
         return dict(rc=rc, num_iters=k, final_normr=nr.value, **{kk: v[:k + 1] for kk, v in hist.items()})
+
+    def verify_solution(self, tol=0.06, whole_domain=False, info=False):
+        g, loc = C.c_double(0), np.zeros(6)
+        rc = self.L.mfo_verify_solution(self.h, tol, int(whole_domain), C.byref(g), loc)
+        return (rc, g.value, loc) if info else rc
 
     # queries
     def nrows(self, r=0): return int(self.L.mfo_nrows(self.h, r))

@@ -325,3 +325,26 @@ def test_cg_history_equals_reference_golden_at_full_size(n, product_lib):
     assert np.uint32(zlib.crc32(p.x.coefs.tobytes())) == g["crc_x"]
     rel = np.abs(h["normr"][1:] - g["normr"][1:]) / g["normr"][1:]
     assert rel.max() <= 1e-8      # the tolerance BASELINE.json states; we are at 0
+
+
+@pytest.mark.parametrize("n,whole", [((10, 10, 10), False), ((6, 5, 7), True), ((32, 32, 32), False), ((12, 12, 12), True)])
+def test_verify_solution_on_device(n, whole, oracle_built, product_lib):
+    """ref/fem/verify_solution.hpp:55-174 evaluated on the device-resident x: same verdict, same worst node, max error
+    within 1e-12 relative of the oracle's (CUDA sin/sinh differ from glibc's in the last bits, so the 90601-term
+    series is not bit-identical; the solution it is compared with is)."""
+    o = Oracle(*n).setup(); o.cg_solve(200, EPS)
+    want_rc, want_max, want = o.verify_solution(0.06, whole, info=True)
+    p = Problem(*n).setup()
+    mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS)
+    rc, gmax, info = mf.verify_solution(p.mesh, None, 0.06, whole, info=True)
+    assert rc == want_rc
+    assert abs(gmax - want_max) <= 1e-12 * max(want_max, 1e-30) + 1e-15, (gmax, want_max)
+    assert info["coords"] == tuple(want[3:6]), (info, want)
+    assert_bits([info["computed"]], [want[1]], "computed value at the worst node")
+    assert abs(info["analytic"] - want[2]) <= 1e-12
+    # tolerance semantics: return code 1 iff max error > tolerance
+    assert mf.verify_solution(p.mesh, None, gmax * 0.5, whole) == 1
+    assert mf.verify_solution(p.mesh, None, gmax * 2.0, whole) == 0
+    # a wrong solution is caught
+    bad = p.x.coefs.copy(); bad[:] = 0.25
+    assert mf.verify_solution(p.mesh, bad, 0.06, False if n[0] >= 10 else whole) == 1

@@ -167,3 +167,35 @@ def test_oracle_equals_reference_multirank(n, npr, oracle_built):
     assert beq(h["normr"], d["normr_hist"][0])
     for r in range(npr):
         assert beq(o.x(r), d["x"][r])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("n,whole", [((10, 10, 10), False), ((6, 5, 7), True), ((20, 20, 20), False)])
+def test_verify_solution_vs_reference(n, whole, oracle_built):
+    """ref/fem/verify_solution.hpp only reports a return code; bisecting the tolerance against the UNMODIFIED
+    reference pins the oracle's max error (and with it analytic_soln) to the last bit."""
+    o = Oracle(*n).setup(); o.cg_solve(200, EPS)
+    r = Ref(*n).setup(); r.cg_solve(200, EPS, trace=False)
+    assert beq(o.x(), r.x())
+    rc, gmax, info = o.verify_solution(0.06, whole, info=True)
+    assert rc == r.verify_solution(0.06, whole)          # coarse whole-domain runs legitimately fail the 0.06 test
+    assert gmax > 0 and info[0] == gmax
+    # the reference returns 1 exactly when max_err > tolerance: flips between nextafter(gmax, 0) and gmax
+    assert r.verify_solution(float(np.nextafter(gmax, 0.0)), whole) == 1
+    assert r.verify_solution(gmax, whole) == 0
+    assert o.verify_solution(float(np.nextafter(gmax, 0.0)), whole) == 1 and o.verify_solution(gmax, whole) == 0
+
+
+def test_verify_solution_multirank_equals_serial(oracle_built):
+    """the verdict does not depend on the partition (MPI_Allreduce MAX, verify_solution.hpp:148-154) when x is the same"""
+    o1 = Oracle(8, 8, 8).setup(); o1.cg_solve(200, EPS)
+    _, g1, i1 = o1.verify_solution(0.06, True, info=True)
+    o4 = Oracle(8, 8, 8, 4).setup()
+    x = o1.x()
+    for rk in range(4):
+        bx = np.zeros(6, np.int32); o4.L.mfo_get_box(o4.h, rk, bx)
+        hi = [int(bx[2 * a + 1]) + (1 if bx[2 * a + 1] == 8 else 0) for a in range(3)]      # owned nodes: +1 on the global high side
+        ids = [ix + 9 * (iy + 9 * iz) for iz in range(bx[4], hi[2]) for iy in range(bx[2], hi[1]) for ix in range(bx[0], hi[0])]
+        o4.L.mfo_set_x(o4.h, rk, np.ascontiguousarray(x[ids]))
+    _, g4, i4 = o4.verify_solution(0.06, True, info=True)
+    assert g1 == g4 and np.array_equal(i1, i4)
