@@ -28,6 +28,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 EPS = float(np.finfo(np.float64).eps)
 MAX_ITERS = 200
+PDL_DEFAULT = 0
 
 
 def weak_dims(nx, ngpus):
@@ -190,6 +191,7 @@ def main():
     ap.add_argument("--dot-mode", type=int, default=0)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange and dot all-reduce over NVLink peer stores "
                     "(default; falls back to NCCL when CUDA IPC is unavailable) or over NCCL send/recv + allgather")
+    ap.add_argument("--pdl", type=int, default=PDL_DEFAULT, help="programmatic dependent launch of the CG-loop kernels (1/0)")
     ap.add_argument("--no-overlap", action="store_true", help="peer mode: do not overlap the halo exchange with the interior SpMV tiles")
     ap.add_argument("--op-timing", type=int, default=2, help="CUDA events inside the timed solves: 2 = around every SpMV launch (roofline), 1 = every op class, 0 = none")
     args = ap.parse_args()
@@ -227,6 +229,7 @@ def main():
     mesh.set_op_timing(args.op_timing)
     mesh.set_option("comm_mode", 1 if args.comm == "peer" else 0)
     mesh.set_option("overlap", 0 if args.no_overlap else 1)
+    mesh.set_option("pdl", args.pdl)
 
     A = mf.CSRMatrix()
     t_setup = time.time()
@@ -348,7 +351,7 @@ def main():
                        "comm": (None if world == 1 else ("NCCL send/recv + allgather" if args.comm == "nccl" else
                                 "NVLink peer stores (halo + dot all-reduce)%s" % ("" if args.no_overlap else ", halo overlapped with the interior SpMV tiles"))),
                        "l2": "inputs larger than L2 (%.1f GB per iteration per GPU vs 126 MB)" % ((12.0 * nnz + 116.0 * nrows) / 1e9), "dot": ["exact (order-reproducing)", "serial", "tree"][args.dot_mode],
-                       "flop_model": "ref/src/driver.hpp:322-341"},
+                       "flop_model": "ref/src/driver.hpp:322-341", "pdl": bool(args.pdl)},
             "hbm_gbs": hbm_gbs, "hbm_gbs_per_gpu": hbm_gbs / world, "pct_of_8TBs_per_gpu": 100.0 * hbm_gbs / world / 8000.0,
             "ms_per_cg_iteration": t_step * 1e3 / max(iters, 1), "cg_times": cg_times,
             "setup_ms": {"structure": mesh.phase_ms("structure"), "assembly": mesh.phase_ms("assembly"), "assembly_elem": mesh.phase_ms("assembly_elem"),

@@ -145,6 +145,7 @@ struct mfe_ctx {
   PeerComm peer;
   int comm_mode = 1;             // 1: NVLink peer stores when available (default), 0: NCCL send/recv + allgather
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
+  int pdl = 0;                   // programmatic dependent launch of the CG-loop kernels (launch_cg)
   int64_t peer_timeout_ms = 30000;
   std::vector<int> send_dst_offset;
   int *d_tiles_boundary = nullptr;          // SpMV tiles that reference external columns (second pass, after the halo)
@@ -168,6 +169,23 @@ static int dev_alloc(T **p, int64_t n)
 }
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+
+// Launch of a CG-loop kernel.  With ctx->pdl the kernel is launched with programmatic stream serialization
+// (programmatic dependent launch): its CTAs may become resident while the previous kernel of the stream drains and
+// run up to their griddepcontrol.wait (first statement of every such kernel), which hides the launch latency and
+// the drain/ramp gap at each of the ~7 kernel boundaries of a CG iteration.
+template <typename... P, typename... A>
+static cudaError_t launch_cg(mfe_ctx *c, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
+  c->launches++;
+  return cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // box_partition: ref/utils/BoxPartition.cpp:79-122 (recursive coordinate bisection, z then y then x)
@@ -657,15 +675,15 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
 // ---------------------------------------------------------------------------------------------------------
 // SpMV configurations: warps per CTA (= tiles in flight per SM), smem stages per warp, gather batches per row
 struct MvCfg { int g, s, h; };
-static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {12, 1, 1}, {14, 1, 1}, {18, 1, 2}, {20, 1, 2}, {21, 1, 2}, {21, 1, 3}, {20, 1, 3} };
+static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {20, 1, 2}, {21, 1, 3} };
 enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
 
-template <int G, int S, int H>
-static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
+template <int G, int S, int H, int MODE>
+static int launch_matvec_mode(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
 {
   static bool attr_set[64] = { false };
   const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 64;
-  auto kern = k_matvec<G, S, H>;
+  auto kern = k_matvec<G, S, H, MODE>;
   if (!attr_set[c->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set[c->device & 63] = true;
@@ -673,10 +691,17 @@ static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_s
   if (!tile_list) nwork = c->ntiles;
   if (nwork <= 0) return 0;
   const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (nwork + G - 1) / G));
-  kern<<<grid, 32 * G, smem, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, tile_base ? tile_base : c->d_tile_base, x, y, c->nrows, c->ntiles, c->nnz_padded, 0,
-                                          with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork);
-  c->launches++;
+  CK(launch_cg(c, kern, dim3(grid), dim3(32 * G), smem, c->d_coefs, c->d_cols, c->d_roff, tile_base ? tile_base : c->d_tile_base, x, y, c->nrows, c->ntiles,
+               c->nnz_padded, 0, with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork));
   return 0;
+}
+
+template <int G, int S, int H>
+static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
+{
+  if (tile_list) return launch_matvec_mode<G, S, H, MV_LIST>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+  if (tile_base) return launch_matvec_mode<G, S, H, MV_SKIP>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+  return launch_matvec_mode<G, S, H, MV_ALL>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
 }
 
 static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k,
@@ -686,13 +711,8 @@ static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with
     case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
     case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
     case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 3: return launch_matvec_cfg<12, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 4: return launch_matvec_cfg<14, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 5: return launch_matvec_cfg<18, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 6: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 7: return launch_matvec_cfg<21, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 8: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 9: return launch_matvec_cfg<20, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 3: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 4: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
   }
   return fail("bad matvec configuration %d", c->mv_cfg);
 }
@@ -704,7 +724,7 @@ static bool use_peer(const mfe_ctx *c) { return c->nranks > 1 && c->comm_mode ==
 static int exchange_nccl(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 {
   const int nsend = (int)c->elements_to_send.size();
-  if (nsend > 0) { k_pack<<<grid_for(nsend, 256), 256, 0, c->stream>>>(x, c->d_elements_to_send, nsend, c->d_send_buf, gate, k); c->launches++; }
+  if (nsend > 0) CK(launch_cg(c, k_pack, dim3(grid_for(nsend, 256)), dim3(256), 0, x, c->d_elements_to_send, nsend, c->d_send_buf, gate, k));
   CKN(g_nccl.GroupStart());
   int64_t ro = c->nrows, so = 0;
   for (size_t i = 0; i < c->neighbors.size(); ++i) {
@@ -736,8 +756,7 @@ static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
     so += c->send_length[i]; ++n;
   }
   ph.start[n] = so; ph.n = n;
-  k_pack_peer<<<grid_for(nsend, 256), 256, 0, c->stream>>>(x, c->d_elements_to_send, nsend, ph, epoch, c->peer.d_ticket, gate, k);
-  c->launches++;
+  CK(launch_cg(c, k_pack_peer, dim3(grid_for(nsend, 256)), dim3(256), 0, x, c->d_elements_to_send, nsend, ph, epoch, c->peer.d_ticket, gate, k));
   return 0;
 }
 // second half (peer mode): wait for the neighbours' stores of this epoch and fill the external tail of x
@@ -753,9 +772,8 @@ static int exchange_end(mfe_ctx *c, double *x, const CgScalars *gate, int k)
     if (c->recv_length[i] > 0) pw.flag[n++] = peer_halo_flags(c, c->rank) + c->neighbors[i];
   pw.n = n;
   const int grid = std::max(1, std::min(32, (n_ext + 2047) / 2048));
-  k_halo_wait_copy<<<grid, 256, 0, c->stream>>>(pw, epoch, peer_halo_buf(c, c->rank, epoch), x + c->nrows, n_ext,
-                                                (unsigned long long)c->peer_timeout_ms * 1000000ULL, c->peer.d_err, gate, k);
-  c->launches++;
+  CK(launch_cg(c, k_halo_wait_copy, dim3(grid), dim3(256), 0, pw, epoch, peer_halo_buf(c, c->rank, epoch), x + c->nrows, n_ext,
+               (unsigned long long)c->peer_timeout_ms * 1000000ULL, c->peer.d_err, gate, k));
   return 0;
 }
 static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
@@ -780,8 +798,7 @@ static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, S
 {
   const int64_t n2 = std::max<int64_t>(1, n / 2);
   const int grid = (int)std::min<int64_t>((n2 + 255) / 256, (int64_t)c->sm_count * 16);
-  k_waxpby<<<grid, 256, 0, c->stream>>>(n, a, x, b, y, w, gate, k);
-  c->launches++;
+  launch_cg(c, k_waxpby, dim3(grid), dim3(256), 0, n, a, x, b, y, w, gate, k);
 }
 
 template <bool SAME, int NW>
@@ -801,8 +818,7 @@ static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const dou
   grid = std::max<int64_t>(grid, (npieces + DOT_MAPS_MAX_PP - 1) / DOT_MAPS_MAX_PP);
   const int PP = (int)((npieces + grid - 1) / grid);
   grid = (npieces + PP - 1) / PP;
-  kern<<<(unsigned)grid, 32 * NW, smem, c->stream>>>(n, x, y, w, (int)npieces, PP, gate, k);
-  c->launches++;
+  CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
   return 0;
 }
 
@@ -838,28 +854,23 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
   w.piece_sums = sums_kind == 2 ? c->dot.piece_sums_b : c->dot.piece_sums_a;
   bool finished = false;                          // global sum + epilogue already done by the local kernel
   if (c->dot_mode == MFE_DOT_SERIAL) {
-    k_dot_serial<<<1, 1, 0, c->stream>>>(n, x, y, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
-    c->launches++;
+    CK(launch_cg(c, k_dot_serial, dim3(1), dim3(1), 0, n, x, y, w.result, sc, epi_local, k, nh, rh, ph, ah, gate));
   } else {
-    if (sums_kind == 0 && nchunks > 0) { k_chunk_sums<<<nchunks, DOT_CTA_THREADS, 0, c->stream>>>(n, x, y, w.piece_sums, w.chunk_sums, gate, k); c->launches++; }
+    if (sums_kind == 0 && nchunks > 0) CK(launch_cg(c, k_chunk_sums, dim3(nchunks), dim3(DOT_CTA_THREADS), 0, n, x, y, w.piece_sums, w.chunk_sums, gate, k));
     if (c->dot_mode == MFE_DOT_TREE) {
-      k_chunk_prefix<<<1, 1024, 0, c->stream>>>(w.chunk_sums, nchunks, w.chunk_prefix, gate, k);
-      k_dot_tree_finish<<<1, 1, 0, c->stream>>>(w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate);
-      c->launches += 2;
+      CK(launch_cg(c, k_chunk_prefix, dim3(1), dim3(1024), 0, w.chunk_sums, nchunks, w.chunk_prefix, gate, k));
+      CK(launch_cg(c, k_dot_tree_finish, dim3(1), dim3(1), 0, w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate));
     } else {
       if (launch_dot_maps(c, n, x, y, w, gate, k)) return 1;
-      k_dot_walk<<<1, WALK_THREADS, 0, c->stream>>>(n, x, y, w, sc, peer ? epi : epi_local, k, nh, rh, ph, ah, gate, pd);
-      c->launches++;
+      CK(launch_cg(c, k_dot_walk, dim3(1), dim3(WALK_THREADS), 0, n, x, y, w, sc, peer ? epi : epi_local, k, nh, rh, ph, ah, gate, pd));
       finished = peer;
     }
   }
   if (multi && peer && !finished) {
-    k_dot_peer_finish<<<1, 32, 0, c->stream>>>(w.result, sc, epi, k, nh, rh, ph, ah, gate, pd);
-    c->launches++;
+    CK(launch_cg(c, k_dot_peer_finish, dim3(1), dim3(32), 0, w.result, sc, epi, k, nh, rh, ph, ah, gate, pd));
   } else if (multi && !peer) {
     CKN(g_nccl.AllGather(w.result, c->d_gather, 1, NCCL_FLOAT64, c->comm, c->stream));
-    k_dot_allreduce_finish<<<1, 1, 0, c->stream>>>(c->d_gather, c->nranks, w.result, sc, epi, k, nh, rh, ph, ah, gate);
-    c->launches++;
+    CK(launch_cg(c, k_dot_allreduce_finish, dim3(1), dim3(1), 0, c->d_gather, c->nranks, w.result, sc, epi, k, nh, rh, ph, ah, gate));
   }
   return 0;
 }
@@ -967,9 +978,8 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
       }
       resume_phase = 0;
       ot.begin(MFE_WAXPY);                                                                                               // (:211-212)
-      k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.piece_sums_a, c->dot.chunk_sums_a,
-                                                                             c->dot.piece_sums_b, c->dot.chunk_sums_b, sc, k);
-      c->launches++;
+      CK(launch_cg(c, k_xr_update, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.piece_sums_a,
+                   c->dot.chunk_sums_a, c->dot.piece_sums_b, c->dot.chunk_sums_b, sc, k));
       ot.end(MFE_WAXPY);
     }
     if (read_scalars(c, &h)) return 1;
@@ -1123,6 +1133,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
     return 0;
   }
   if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
+  if (!strcmp(name, "pdl")) { c->pdl = value != 0; return 0; }
   if (!strcmp(name, "peer_timeout_ms")) { if (value < 1) return fail("mfe_set_option: peer_timeout_ms < 1"); c->peer_timeout_ms = value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
@@ -1344,7 +1355,7 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
     if (!strcmp(what, "waxpby")) { launch_waxpby(c, n, one, c->d_r, half, c->d_p, c->d_tmp1, nullptr, 0); return 0; }
     if (!strcmp(what, "dot_rr")) return launch_dot(c, n, c->d_r, c->d_r, 0, EPI_NONE, 0, false, nullptr);
     if (!strcmp(what, "dot_pap")) return launch_dot(c, n, c->d_Ap, c->d_p, 0, EPI_NONE, 0, false, nullptr);
-    if (!strcmp(what, "xr_update")) { k_xr_update<<<grid_for(n, DOT_CHUNK), DOT_CTA_THREADS, 0, c->stream>>>(n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.piece_sums_a, c->dot.chunk_sums_a, nullptr, nullptr, nullptr, 0); c->launches++; return 0; }
+    if (!strcmp(what, "xr_update")) { CK(launch_cg(c, k_xr_update, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.piece_sums_a, c->dot.chunk_sums_a, nullptr, nullptr, nullptr, 0)); return 0; }
     (void)rep;
     return fail("mfe_time_kernel: unknown kernel '%s'", what);
   };

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_xr_update(int64_t n, const 
                                                                double *__restrict__ chunk_sums, double *__restrict__ zero_piece_sums,
                                                                double *__restrict__ zero_chunk_sums, const CgScalars *gate, int k)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ double sh[DOT_PIECES_PER_CHUNK];
   const double alpha = sc->alpha, nalpha = sc->neg_alpha, one = 1.0;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_chunk_sums(int64_t n, const
                                                                 double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
                                                                 const CgScalars *gate, int k)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ double sh[DOT_PIECES_PER_CHUNK];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_chunk_sums(int64_t n, const
 __global__ void __launch_bounds__(1024) k_chunk_prefix(const double *__restrict__ sums, int nchunks, double *__restrict__ chunk_prefix,
                                                        const CgScalars *gate, int k)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ double wtot[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -222,7 +225,7 @@ template <bool SAME, int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
 k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y, DotWork w, int npieces, int PP, const CgScalars *gate, int k)
 {
-  if (cg_gate_closed(gate, k)) return;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // PDL: see launch_cg (api.cu)
   constexpr int STAGE = DotMapsCfg<SAME, NW>::STAGE_BYTES;
   constexpr int NT = 32 * NW;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -251,6 +254,8 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
   }
   for (int i = tid; i < DotMapsCfg<SAME, NW>::MAX_CHUNKS; i += NT) ccnt[i] = 0;
   __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");                    // the operands, sums and gate scalars are final from here on
+  if (cg_gate_closed(gate, k)) return;
   if (lane == 0 && wq < np) issue(p0 + wq);                     // first piece of every warp is in flight during the prologue
 
   // ---- prologue: predicted running sum at the start of every piece of this CTA ----
@@ -416,6 +421,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
                                                           double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
                                                           const CgScalars *gate, PeerDot pd)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ int dirty[DOT_MAX_DIRTY];
   __shared__ int sorted[DOT_MAX_DIRTY];
@@ -506,6 +512,7 @@ __global__ void k_dot_serial(int64_t n, const double *__restrict__ x, const doub
                              int epi, int k, double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
                              const CgScalars *gate)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const double s = dot_replay(x, y, 0, n, 0.0);
   *result = s;
@@ -515,6 +522,7 @@ __global__ void k_dot_serial(int64_t n, const double *__restrict__ x, const doub
 __global__ void k_dot_tree_finish(const double *chunk_prefix, int nchunks, double *result, CgScalars *sc, int epi, int k,
                                   double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist, const CgScalars *gate)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const double s = chunk_prefix[nchunks];
   *result = s;
@@ -524,6 +532,7 @@ __global__ void k_dot_tree_finish(const double *chunk_prefix, int nchunks, doubl
 __global__ void __launch_bounds__(32) k_dot_peer_finish(double *result, CgScalars *sc, int epi, int k, double *normr_hist, double *rtrans_hist,
                                                         double *pap_hist, double *alpha_hist, const CgScalars *gate, PeerDot pd)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   bool ok = true;
   const double g = peer_dot_allreduce(pd, threadIdx.x == 0 ? *result : 0.0, ok);
@@ -539,6 +548,7 @@ __global__ void __launch_bounds__(32) k_dot_peer_finish(double *result, CgScalar
 __global__ void k_dot_allreduce_finish(const double *gathered, int nranks, double *result, CgScalars *sc, int epi, int k,
                                        double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist, const CgScalars *gate)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   double g = gathered[0];
   for (int p = 1; p < nranks; ++p) g = __dadd_rn(g, gathered[p]);

@@ -12,6 +12,10 @@
 // associative, so a run of terms collapses to one DotMap by a parallel ordered reduction -- provided the sum
 // never leaves the binade inside the run.  That proviso is tracked conservatively with (lo,hi), the extreme
 // intermediate offsets, and checked against the actual S when the map is applied.
+// A run whose terms are all >= 0 relative to the sign of the sum can never dip below its entry value, whatever S
+// is -- in particular when S sits EXACTLY on the lower binade boundary (S = 2^52: the running sum is a power of
+// two, which miniFE's first dots produce: r = b holds exact 1.0s followed by long runs of zeros).  Such runs carry
+// lo = 1, the tightest bound that dot_apply's test  S + lo >= 2^52 + 1  accepts for every S; composition keeps it.
 //
 // The binade ("hypothesis") for each leaf of LEAF consecutive terms is predicted from a conventional
 // floating-point prefix sum (accurate to ~1e-16 relative, more than enough to name the binade away from its
@@ -117,6 +121,13 @@ MFE_HD bool dot_term_offsets(double p, int hyp, long long &t0, long long &t1)
   return true;
 }
 
+// the term does not pull the running sum towards zero: it is zero or has the sign of the sum
+MFE_HD bool dot_term_nonneg(double p, int hyp)
+{
+  const uint64_t u = MFE_D2U(p);
+  return (u << 1) == 0 || ((u >> 63) != 0) == (((hyp >> 11) & 1) != 0);
+}
+
 // append one term to a map (the map of a run followed by the term)
 MFE_HD void dot_append(DotMap &m, long long t0, long long t1)
 {
@@ -150,6 +161,7 @@ MFE_HD DotMap dot_zero_map()
   DotMap m; m.a0 = 0; m.a1 = 0; m.lo = 0; m.hi = 0; m.hyp = HYP_ZERO; m.pad = 0; return m;
 }
 MFE_HD bool dot_is_zero(double p) { return (MFE_D2U(p) << 1) == 0; }
+MFE_HD unsigned dot_hi32(double v) { return (unsigned)(MFE_D2U(v) >> 32); }
 
 MFE_HD DotMap dot_leaf_map(const double *x, const double *y, long long begin, long long end, int hyp)
 {
@@ -161,11 +173,15 @@ MFE_HD DotMap dot_leaf_map(const double *x, const double *y, long long begin, lo
   }
   DotMap m = dot_identity();
   m.hyp = hyp;
+  bool nonneg = true;
   for (long long i = begin; i < end; ++i) {
     long long t0, t1;
-    if (!dot_term_offsets(MFE_DMUL(x[i], y[i]), hyp, t0, t1)) return dot_invalid();
+    const double p = MFE_DMUL(x[i], y[i]);
+    if (!dot_term_offsets(p, hyp, t0, t1)) return dot_invalid();
+    nonneg = nonneg && dot_term_nonneg(p, hyp);
     dot_append(m, t0, t1);
   }
+  if (nonneg) m.lo = 1;
   return m;
 }
 // same from precomputed products
@@ -179,11 +195,14 @@ MFE_HD DotMap dot_leaf_map_products(const double *prod, int n, int hyp)
   }
   DotMap m = dot_identity();
   m.hyp = hyp;
+  bool nonneg = true;
   for (int i = 0; i < n; ++i) {
     long long t0, t1;
     if (!dot_term_offsets(prod[i], hyp, t0, t1)) return dot_invalid();
+    nonneg = nonneg && dot_term_nonneg(prod[i], hyp);
     dot_append(m, t0, t1);
   }
+  if (nonneg) m.lo = 1;
   return m;
 }
 
@@ -209,6 +228,7 @@ MFE_HD double dot_fmax(double a, double b) { return a > b ? a : b; }
     const double v = MFE_DMUL(MFE_DMUL((p), c1), c2);                                                       \
     const double av = fabs(v);                                                                              \
     vmax = av > vmax ? av : vmax;                                                                           \
+    sg |= dot_hi32(v) & (dot_is_zero(v) ? 0u : 0x80000000u);   /* a NEGATIVE scaled term (v = -0.0 is harmless) */ \
     const double r = rint(v);                                                                               \
     if (fabs(v - r) == 0.5) {                              /* exact tie: even candidate r, odd 2v - r */  \
       const double o = MFE_DADD(MFE_DADD(v, v), -r);                                                        \
@@ -233,6 +253,7 @@ MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
   const double c1 = dot_pow2(k1);
   const double c2 = ((hyp >> 11) & 1) ? -dot_pow2(k2) : dot_pow2(k2);   // offsets relative to the sign of the sum
   double A0 = 0.0, A1 = 0.0, lo = 1.152921504606846976e18, hi = -1.152921504606846976e18, vmax = 0.0, nt = 0.0;
+  unsigned sg = 0;
   if (n == DOT_LEAF) {
 #ifdef __CUDA_ARCH__
 #pragma unroll
@@ -242,6 +263,7 @@ MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
     for (int i = 0; i < n; ++i) MFE_DOT_FP_TERM(prod[i])
   }
   lo -= nt; hi += nt;
+  if (!(sg >> 31)) lo = 1.0;                          // no term pulls towards zero: the run never dips below its entry value
   // |v| >= 2^52 (or inf): the term alone leaves the binade.  nan: A0 is nan.  dot_apply needs 2^52 < S + lo and
   // S + hi < 2^53 with 2^52 <= S < 2^53, so a usable map has |lo|,|hi| < 2^52.
   if (!(vmax < 4503599627370496.0) || !(A0 == A0) || !(A1 == A1) || !(lo > -4503599627370496.0 && hi < 4503599627370496.0))
@@ -254,7 +276,6 @@ MFE_HD DotMap dot_leaf_map_products_fp(const double *prod, int n, int hyp)
 // Fast path of the fp formulation for the common leaf: no exact tie, all offsets of one sign.  Then a0 == a1, the
 // partial offsets are monotone, and lo/hi are the first and last partial offsets -- no per-term min/max needed
 // (FP64 min/max costs ~6 instructions on sm_100).  Anything else falls back to dot_leaf_map_products_fp.
-MFE_HD unsigned dot_hi32(double v) { return (unsigned)(MFE_D2U(v) >> 32); }
 
 // Full leaf (DOT_LEAF products), everything unrolled so that `prod` can live in registers on the device.
 MFE_HD DotMap dot_leaf_map16_fp(const double *prod, int hyp)
@@ -264,11 +285,13 @@ MFE_HD DotMap dot_leaf_map16_fp(const double *prod, int hyp)
   const double c1 = dot_pow2(k1);
   const double c2 = ((hyp >> 11) & 1) ? -dot_pow2(k2) : dot_pow2(k2);
   double A0 = 0.0, A1 = 0.0, lo = 1.152921504606846976e18, hi = -1.152921504606846976e18, vmax = 0.0, nt = 0.0;
+  unsigned sg = 0;
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
   for (int i = 0; i < DOT_LEAF; ++i) MFE_DOT_FP_TERM(prod[i])
   lo -= nt; hi += nt;
+  if (!(sg >> 31)) lo = 1.0;
   if (!(vmax < 4503599627370496.0) || !(A0 == A0) || !(A1 == A1) || !(lo > -4503599627370496.0 && hi < 4503599627370496.0))
     return dot_invalid();
   DotMap m;
@@ -284,29 +307,39 @@ MFE_HD DotMap dot_leaf_map16_fp(const double *prod, int hyp)
 // the binade; otherwise the function returns false and the caller takes the exact formulation
 // (dot_leaf_map16_fp).  A wrong prediction therefore costs time, never correctness.
 // Returns true and (a, lo, hi) as exact integers held in doubles.  Requires hyp >= 0 and hyp != HYP_ZERO.
-// |v| >= 2^52, inf and nan all surface in absum (= sum of |rint(v)|), so no per-term range check is needed.
+// |v| >= 2^51, inf and nan all surface in absum (= sum of the |rounded offsets|), so no per-term range check is needed.
 #define MFE_DOT_FAR_MARGIN 16777216.0   /* 2^24 ulps ~ 4e-9 relative; the prediction is good to ~1e-13 */
+// Rounding to the nearest integer (ties to even) is done with the 1.5 * 2^52 trick -- (v + M) - M, exact for
+// |v| < 2^51 -- instead of rint(): two FP64 adds, no conversion-pipe instruction.  For |v| >= 2^51 the trick no
+// longer rounds correctly, but then |r| >= 2^51 - 1 and the absum < 2^51 test below rejects the leaf.  The offsets
+// are exact integers, so their sums are order independent and kept in four partial accumulators (short dependent
+// chains; the GPU kernel is latency bound on exactly these chains).
+#define MFE_DOT_RNE_MAGIC 6755399441055744.0   /* 1.5 * 2^52 */
+#define MFE_DOT_SIMPLE_TERM(k, vexpr)                                                                      \
+  {                                                                                                         \
+    const double v = (vexpr);                                                                               \
+    const double r = MFE_DADD(MFE_DADD(v, MFE_DOT_RNE_MAGIC), -MFE_DOT_RNE_MAGIC);                          \
+    const double d = MFE_DADD(v, -r);                                                                       \
+    A[k] = MFE_DADD(A[k], r);                                                                               \
+    AB[k] = MFE_DADD(AB[k], fabs(r));                                                                       \
+    const unsigned hd = dot_hi32(d) & 0x7fffffffu;                                                          \
+    dm[k] = hd > dm[k] ? hd : dm[k];                                                                        \
+    sg |= dot_hi32(v);                     /* sign bits of the scaled terms (-0.0 counts as negative: harmless) */ \
+  }
 MFE_HD bool dot_leaf16_simple(const double *prod, int hyp, double pre, double &a, double &lo, double &hi)
 {
   const int k = 1075 - (hyp & 0x7ff);                 // v = p * 2^k, k in [-971, 1074]
   const bool neg = ((hyp >> 11) & 1) != 0;
-  double A = 0.0, absum = 0.0, Sp;
-  unsigned dmax = 0;                                  // max high word of |v - rint(v)|: 0x3fe00000 <=> an exact tie
+  double A[4] = { 0.0, 0.0, 0.0, 0.0 }, AB[4] = { 0.0, 0.0, 0.0, 0.0 }, Sp;
+  unsigned dm[4] = { 0, 0, 0, 0 };                    // max high word of |v - r|: 0x3fe00000 <=> an exact tie
+  unsigned sg = 0;
   if (k <= 1023) {                                    // 2^k is a normal double: one exact scaling
     const double c = neg ? -dot_pow2(k) : dot_pow2(k);
     Sp = MFE_DMUL(pre, c);
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int i = 0; i < DOT_LEAF; ++i) {
-      const double v = MFE_DMUL(prod[i], c);
-      const double r = rint(v);
-      const double d = v - r;
-      A += r;
-      absum += fabs(r);
-      const unsigned hd = dot_hi32(d) & 0x7fffffffu;
-      dmax = hd > dmax ? hd : dmax;
-    }
+    for (int i = 0; i < DOT_LEAF; ++i) MFE_DOT_SIMPLE_TERM(i & 3, MFE_DMUL(prod[i], c))
   } else {
     const int k1 = k / 2, k2 = k - k1;
     const double c1 = dot_pow2(k1);
@@ -315,22 +348,22 @@ MFE_HD bool dot_leaf16_simple(const double *prod, int hyp, double pre, double &a
 #ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
-    for (int i = 0; i < DOT_LEAF; ++i) {
-      const double v = MFE_DMUL(MFE_DMUL(prod[i], c1), c2);
-      const double r = rint(v);
-      const double d = v - r;
-      A += r;
-      absum += fabs(r);
-      const unsigned hd = dot_hi32(d) & 0x7fffffffu;
-      dmax = hd > dmax ? hd : dmax;
-    }
+    for (int i = 0; i < DOT_LEAF; ++i) MFE_DOT_SIMPLE_TERM(i & 3, MFE_DMUL(MFE_DMUL(prod[i], c1), c2))
   }
-  // absum < 2^52 bounds every |rint(v)|, |A|, pos and -neg (and rejects inf / nan)
-  if (!(dmax < 0x3fe00000u && absum < 4503599627370496.0)) return false;
-  const double pos = (absum + A) * 0.5, ng = (A - absum) * 0.5;     // exact: absum +- A are even integers < 2^53
-  const bool far = (Sp + ng) - MFE_DOT_FAR_MARGIN > 4503599627370496.0 && (Sp + pos) + MFE_DOT_FAR_MARGIN < 9007199254740992.0;
+  const double Asum = MFE_DADD(MFE_DADD(A[0], A[1]), MFE_DADD(A[2], A[3]));
+  const double absum = MFE_DADD(MFE_DADD(AB[0], AB[1]), MFE_DADD(AB[2], AB[3]));
+  unsigned dmax = dm[0] > dm[1] ? dm[0] : dm[1];
+  const unsigned dmax2 = dm[2] > dm[3] ? dm[2] : dm[3];
+  dmax = dmax > dmax2 ? dmax : dmax2;
+  // absum < 2^51 bounds every |r|, |A|, pos and -neg, keeps the rounding trick exact, and rejects inf / nan
+  if (!(dmax < 0x3fe00000u && absum < 2251799813685248.0)) return false;
+  const double pos = (absum + Asum) * 0.5, ng = (Asum - absum) * 0.5;     // exact: absum +- A are even integers < 2^53
+  // no term pulls towards zero: the low end of the binade cannot be crossed (lo = 1, see the header); this is what
+  // keeps a running sum that sits exactly on a power of two (S = 2^52) out of the slow path
+  const bool nonneg = !(sg >> 31);
+  const bool far = (nonneg || (Sp + ng) - MFE_DOT_FAR_MARGIN > 4503599627370496.0) && (Sp + pos) + MFE_DOT_FAR_MARGIN < 9007199254740992.0;
   if (!far) return false;
-  a = A; lo = ng; hi = pos;
+  a = Asum; lo = nonneg ? 1.0 : ng; hi = pos;
   return true;
 }
 
@@ -346,7 +379,8 @@ MFE_HD bool dot_leaf_risky(const DotMap &m, int hyp, double pre)
   const int k = 1075 - (hyp & 0x7ff);
   const int k1 = k / 2, k2 = k - k1;
   const double Sp = fabs(MFE_DMUL(MFE_DMUL(pre, dot_pow2(k1)), dot_pow2(k2)));     // |pre| / ulp, in [2^52, 2^53)
-  return !((Sp + (double)m.lo) - MFE_DOT_RISK_MARGIN > 4503599627370496.0 && (Sp + (double)m.hi) + MFE_DOT_RISK_MARGIN < 9007199254740992.0);
+  const bool lo_safe = m.lo >= 1 || (Sp + (double)m.lo) - MFE_DOT_RISK_MARGIN > 4503599627370496.0;
+  return !(lo_safe && (Sp + (double)m.hi) + MFE_DOT_RISK_MARGIN < 9007199254740992.0);
 }
 
 MFE_HD DotMap dot_leaf_map16(const double *prod, int hyp, double pre)

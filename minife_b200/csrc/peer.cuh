@@ -79,6 +79,7 @@ struct PeerHalo {                               // by-value kernel argument
 __global__ void __launch_bounds__(256) k_pack_peer(const double *__restrict__ x, const int *__restrict__ elements_to_send, int nsend,
                                                    PeerHalo ph, unsigned long long epoch, unsigned int *ticket, const CgScalars *gate, int k)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nsend) {
@@ -108,6 +109,7 @@ struct PeerWait {
 __global__ void __launch_bounds__(256) k_halo_wait_copy(PeerWait pw, unsigned long long epoch, const double *halo, double *__restrict__ x_tail,
                                                         int n_ext, unsigned long long timeout_ns, int *err, const CgScalars *gate, int k)
 {
+  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;

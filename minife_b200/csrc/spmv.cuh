@@ -43,18 +43,24 @@ __device__ __forceinline__ void dadd_if(double &sum, double prod, int u, int len
   asm volatile("{\n.reg .pred p;\nsetp.lt.s32 p, %2, %3;\n@p add.rn.f64 %0, %0, %1;\n}\n" : "+d"(sum) : "d"(prod), "r"(u), "r"(len));
 }
 
-template <int G, int S, int H>
+// MODE: MV_ALL = every tile in natural order (single GPU, or no overlap); MV_SKIP = natural order, tiles whose
+// tile_base carries MV_SKIP_BIT are skipped (interior pass); MV_LIST = work item i is tile tile_list[i] (boundary pass)
+enum { MV_ALL = 0, MV_SKIP = 1, MV_LIST = 2 };
+
+template <int G, int S, int H, int MODE>
 __global__ void __launch_bounds__(32 * G, 1)
 k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
          const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
          int64_t ntiles, int64_t nnz_padded, int zmask, double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
          const CgScalars *gate, int k, const int *__restrict__ tile_list, int64_t nwork)
 {
+  // Programmatic dependent launch: everything up to griddepcontrol.wait below touches only the matrix (static
+  // during a solve), so the first tiles are already streaming in while the previous kernel (the p update) drains.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   // tile_list == nullptr: all tiles 0 .. ntiles-1 (nwork == ntiles).  Otherwise work item i is tile tile_list[i]
   // (the boundary tiles of a rank, after the halo arrived).  The interior pass that overlaps the halo exchange runs
   // over all tiles in natural order with a FLAGGED copy of tile_base: bit 62 of tile_base[t] set = skip tile t
   // (it references external columns), so the flag costs no extra load on the TMA issue path.
-  if (cg_gate_closed(gate, k)) return;
   constexpr int TR = MV_TILE_ROWS;
   constexpr int CAP = MatvecCfg::CAP;
   constexpr int SLOT = MatvecCfg::SLOT_BYTES;
@@ -69,21 +75,23 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   uint64_t pol_stream = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   const int64_t stride = (int64_t)gridDim.x * G;      // this warp's work items: (blockIdx.x + j * gridDim.x) * G + w
-  auto tile_of = [&](int64_t i) -> int64_t { return tile_list ? (int64_t)tile_list[i] : i; };
+  auto tile_of = [&](int64_t i) -> int64_t { return MODE == MV_LIST ? (int64_t)tile_list[i] : i; };
+  constexpr int64_t SKIP = MODE == MV_SKIP ? MV_SKIP_BIT : 0;
 
-  auto issue = [&](int64_t t, int s) {
+  auto issue = [&](int64_t t, int s) -> bool {
     const int64_t b0 = tile_base[t];
-    if (b0 & MV_SKIP_BIT) return;                       // skipped in this pass: nothing to stage
+    if (b0 & SKIP) return false;                        // skipped in this pass: nothing to stage
     const int64_t a0 = b0 & ~3LL;
-    int64_t a1 = ((tile_base[t + 1] & ~MV_SKIP_BIT) + 3) & ~3LL;
+    int64_t a1 = ((tile_base[t + 1] & ~SKIP) + 3) & ~3LL;
     if (a1 > nnz_padded) a1 = nnz_padded;
     const int64_t n = a1 - a0;
-    if (n <= 0 || n > CAP) return;                      // oversized tile: consumers read global memory directly
+    if (n <= 0 || n > CAP) return false;                // oversized tile: consumers read global memory directly
     double *sc = reinterpret_cast<double *>(gbase + (size_t)s * SLOT);
     int *si = reinterpret_cast<int *>(gbase + (size_t)s * SLOT + CAP * 8);
     mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
     bulk_g2s_hint(sc, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
     bulk_g2s_hint(si, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+    return true;
   };
 
   if (lane == 0) {
@@ -94,8 +102,15 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   __syncthreads();
 
   int64_t wi = (int64_t)blockIdx.x * G + w;           // work item
+  unsigned armed0 = 0;
   if (lane == 0)
-    for (int s = 0; s < S; ++s) { const int64_t ii = wi + s * stride; if (ii < nwork) issue(tile_of(ii), s); }
+    for (int s = 0; s < S; ++s) { const int64_t ii = wi + s * stride; if (ii < nwork && issue(tile_of(ii), s)) armed0 |= 1u << s; }
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on x, y, the gate scalars and the sums may be touched
+  if (cg_gate_closed(gate, k)) {                        // iteration switched off: let the copies in flight land, then leave
+    if (lane == 0)
+      for (int s = 0; s < S; ++s) if ((armed0 >> s) & 1u) mbar_wait(&bars[s], 0);
+    return;
+  }
 
   uint32_t phase_bits = 0;            // expected mbarrier parity per stage (flips each time a stage completes)
   // software-pipelined row offsets: (o0,o1) of this lane's row in the NEXT tile are loaded one tile ahead
@@ -113,8 +128,8 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     const int64_t t = tnext;
     const int64_t r = t * TR + lane;
     const uint32_t o0 = o0n, o1 = o1n;
-    const bool skipped = (tb0n & MV_SKIP_BIT) != 0;
-    const int64_t tb0 = tb0n & ~MV_SKIP_BIT, tb1 = tb1n & ~MV_SKIP_BIT;
+    const bool skipped = (tb0n & SKIP) != 0;
+    const int64_t tb0 = tb0n & ~SKIP, tb1 = tb1n & ~SKIP;
     if (wi + stride < nwork) {
       tnext = tile_of(wi + stride);
       const int64_t rn = tnext * TR + lane;
@@ -188,7 +203,7 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
       const int64_t i2 = wi + (int64_t)S * stride;
       if (i2 < nwork) issue(tile_of(i2), s);
       if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
-        if (G == 16 && tile_list == nullptr) {
+        if (G == 16 && MODE != MV_LIST) {
           // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
           // rounds; the warp that completes a round publishes it).  Prediction data: a lagging warp that lets a
           // slot be reused early can only blur a prediction.

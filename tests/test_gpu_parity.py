@@ -132,7 +132,7 @@ def test_matvec_every_configuration_bit_exact(oracle_built, product_lib):
     rng = np.random.default_rng(11)
     x = rng.standard_normal(o.nrows()) * 10.0 ** rng.integers(-3, 4, o.nrows())
     want = o.matvec(x)
-    for cfg in range(10):
+    for cfg in range(5):
         p.mesh.set_option("matvec_config", cfg)
         y = np.full(o.nrows(), 123.0)
         mf.matvec(p.A, x, y)
@@ -348,3 +348,19 @@ def test_verify_solution_on_device(n, whole, oracle_built, product_lib):
     # a wrong solution is caught
     bad = p.x.coefs.copy(); bad[:] = 0.25
     assert mf.verify_solution(p.mesh, bad, 0.06, False if n[0] >= 10 else whole) == 1
+
+
+@pytest.mark.parametrize("n", [(20, 30, 40), (64, 64, 64)])
+def test_cg_history_bit_exact_with_programmatic_dependent_launch(n, oracle_built, product_lib):
+    """launch_cg with the programmatic-serialization attribute (kernels become resident while their predecessor drains and
+    block in griddepcontrol.wait): same bits, and the gated-off iterations after convergence still do nothing."""
+    o = Oracle(*n).setup()
+    want = o.cg_solve(200, EPS)
+    p = Problem(*n).setup()
+    p.mesh.set_option("pdl", 1)
+    for _ in range(2):
+        p.x.coefs[:] = 0.0
+        iters, normr, times, h = mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS, history=True)
+        assert iters == want["num_iters"]
+        assert_bits(h["normr"], want["normr"], "normr history (pdl)")
+        assert_bits(p.x.coefs, o.x(), "solution x (pdl)")
