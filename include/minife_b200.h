@@ -70,6 +70,10 @@ int mfe_make_local_matrix(mfe_ctx *ctx, int64_t *num_cols);
 int mfe_cg_solve(mfe_ctx *ctx, double *x_host, int max_iter, double tolerance, int *num_iters, double *normr,
                  double cg_times[MFE_NUM_TIMERS], double *normr_hist, double *rtrans_hist, double *pap_hist,
                  double *alpha_hist);
+/* ref/src/time_kernels.hpp:42-134 (the MINIFE_KERNELS != 0 branch of driver.hpp:257-270): max_iter x waxpby(1,x,0,x,p),
+ * max_iter x matvec(A,p,x), xdotp = sum over max_iter x dot(x,p), each loop timed (kern_times[WAXPY,MATVEC,DOT]).
+ * x_host: in = x (nrows doubles), out = A*p as the reference leaves it; NULL = device-resident x. */
+int mfe_time_kernels(mfe_ctx *ctx, double *x_host, int max_iter, double *xdotp, double kern_times[MFE_NUM_TIMERS]);
 /* ref/fem/verify_solution.hpp:55-174 (+ analytic_soln.hpp:69-118) on the device-resident x left by mfe_cg_solve
  * (or mfe_import_vector "x"): compares x with the 301x301-term analytic series at the nodes within 0.05 of the
  * cube centre (verify_whole_domain = 0, driver.hpp:296) or at every owned node.  *return_code = the reference's
@@ -81,7 +85,9 @@ int mfe_set_dot_mode(mfe_ctx *ctx, int mode);
 /* knobs: "matvec_config" = index into the SpMV (warps, stages, gather batches) table; "comm_mode" = 1 NVLink peer
  * stores for halo + dot all-reduce (default when every rank can map every other rank's mailbox through CUDA IPC),
  * 0 NCCL send/recv + allgather; "overlap" = 1 run the SpMV tiles that need no halo while the halo is in flight
- * (peer mode); "peer_timeout_ms" = bound of every peer spin (default 30000); "dot_maps_warps" = 0 | 16 | 24 */
+ * (peer mode); "peer_timeout_ms" = bound of every peer spin (default 30000); "dot_maps_warps" = 0 | 16 | 24; "pdl" = 1 launch the
+ * CG-loop kernels with programmatic stream serialization; "fused" = 1 MINIFE_FUSED reporting (cg_solve.hpp:172-176,
+ * 203-206): SpMV + dot(Ap,p) are timed as cg_times[MATVECDOT] (the values are bit-identical either way) */
 int mfe_set_option(mfe_ctx *ctx, const char *name, int64_t value);
 /* CUDA events inside mfe_cg_solve: 1 = around every op class, filling cg_times[WAXPY,DOT,MATVEC] (default);
  * 2 = around the SpMV only (two events per iteration: cg_times[MATVEC]); 0 = none (only TOTAL) */
@@ -120,6 +126,10 @@ int mfe_import_csr(mfe_ctx *ctx, int64_t nrows, int64_t num_cols, const int *row
  * milliseconds per launch over `reps` launches (CUDA events on the launching stream).
  * what: "matvec", "matvec_dot", "waxpby", "dot_rr", "dot_pap", "xr_update", "cg_iteration" */
 int mfe_time_kernel(mfe_ctx *ctx, const char *what, int reps, double *ms_per_launch);
+/* diagnostics of the order-reproducing dot: out[0] dots, [1] sum / [2] max of "dirty" leaves (replayed term by term),
+ * [3] whole-vector replays, [4] gaps that took the slow path, [5] total / [6] max ns in the walk kernel, [7] index of
+ * the slowest dot; from out[16]: a ring of 512 (slow gaps << 32 | dirty leaves, ns) pairs.  Returns the word count. */
+int64_t mfe_dot_stats(mfe_ctx *ctx, uint64_t *out, int64_t cap, int reset);
 /* number of kernel launches issued by this context since creation (bench.py's gpu_launches) */
 int64_t mfe_launch_count(const mfe_ctx *ctx);
 /* phase timings of the last calls, milliseconds: "structure","assembly","assembly_elem","assembly_gather",

@@ -36,6 +36,7 @@ SIGNATURES = {
     "mfe_impose_dirichlet": (C.c_int, [_vp, C.c_double, C.c_int]),
     "mfe_make_local_matrix": (C.c_int, [_vp, _pi64]),
     "mfe_cg_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp]),
+    "mfe_time_kernels": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_double), _vp]),
     "mfe_verify_solution": (C.c_int, [_vp, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp]),
     "mfe_set_dot_mode": (C.c_int, [_vp, C.c_int]),
     "mfe_set_op_timing": (C.c_int, [_vp, C.c_int]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "mfe_import_vector": (C.c_int, [_vp, C.c_char_p, _f64p]),
     "mfe_import_csr": (C.c_int, [_vp, _i64, _i64, _i32p, _i32p, _f64p]),
     "mfe_time_kernel": (C.c_int, [_vp, C.c_char_p, C.c_int, C.POINTER(C.c_double)]),
+    "mfe_dot_stats": (_i64, [_vp, _vp, _i64, C.c_int]),
     "mfe_launch_count": (_i64, [_vp]),
     "mfe_phase_ms": (C.c_double, [_vp, C.c_char_p]),
 }

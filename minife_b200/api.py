@@ -289,3 +289,12 @@ def verify_solution(mesh, x=None, tolerance=0.06, verify_whole_domain=False, inf
     if info:
         return rc.value, gmax.value, dict(err=loc[0], computed=loc[1], analytic=loc[2], coords=tuple(loc[3:6]))
     return rc.value
+
+
+def time_kernels(A, b, x, matvec_op=None, max_iter=500):
+    """ref/src/time_kernels.hpp:42-134 (MINIFE_KERNELS != 0): ``max_iter`` x waxpby(1,x,0,x,p), ``max_iter`` x
+    matvec(A,p,x), ``xdotp`` = sum of ``max_iter`` x dot(x,p).  Returns ``(xdotp, kern_times[NUM_TIMERS])``; ``x.coefs``
+    holds A*p afterwards, as in the reference."""
+    r, times = C.c_double(0), np.zeros(NUM_TIMERS)
+    check(lib().mfe_time_kernels(A._ctx(), _vp(x.coefs) if x is not None else None, int(max_iter), C.byref(r), _vp(times)), "time_kernels")
+    return r.value, times

@@ -146,6 +146,7 @@ struct mfe_ctx {
   int comm_mode = 1;             // 1: NVLink peer stores when available (default), 0: NCCL send/recv + allgather
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
   int pdl = 0;                   // programmatic dependent launch of the CG-loop kernels (launch_cg)
+  int fused = 0;                 // MINIFE_FUSED reporting: SpMV + dot(Ap,p) are timed as MATVECDOT (cg_solve.hpp:172-176)
   int64_t peer_timeout_ms = 30000;
   std::vector<int> send_dst_offset;
   int *d_tiles_boundary = nullptr;          // SpMV tiles that reference external columns (second pass, after the halo)
@@ -300,7 +301,7 @@ static void free_vectors(mfe_ctx *c)
   free_dev(c->dot.chunk_sums_a); free_dev(c->dot.piece_sums_a); free_dev(c->dot.chunk_sums_b); free_dev(c->dot.piece_sums_b);
   free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps); free_dev(c->dot.w.chunk_cnt);
   free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.warp_maps); free_dev(c->dot.w.super_maps); free_dev(c->dot.w.hyper_maps);
-  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result);
+  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.w.stats);
   c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = nullptr;
   c->dot = DotWs();
   c->vec_cap = 0;
@@ -460,7 +461,8 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
       dev_alloc(&c->dot.w.warp_maps, npieces + 8) || dev_alloc(&c->dot.w.super_maps, nchunks / 32 + 2) ||
       dev_alloc(&c->dot.w.hyper_maps, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.chunk_cnt, nchunks + 1) || dev_alloc(&c->dot.w.super_cnt, nchunks / 32 + 2) ||
       dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) ||
-      dev_alloc(&c->dot.w.result, 1)) return 1;
+      dev_alloc(&c->dot.w.result, 1) || dev_alloc(&c->dot.w.stats, DOT_STATS_WORDS)) return 1;
+  CK(cudaMemsetAsync(c->dot.w.stats, 0, 8 * DOT_STATS_WORDS, c->stream));
   CK(cudaMemsetAsync(c->dot.w.dirty_count, 0, sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->dot.w.chunk_cnt, 0, sizeof(int) * (nchunks + 1), c->stream));
   CK(cudaMemsetAsync(c->dot.w.super_cnt, 0, sizeof(int) * (nchunks / 32 + 2), c->stream));
@@ -682,7 +684,7 @@ template <int G, int S, int H, int MODE>
 static int launch_matvec_mode(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
 {
   static bool attr_set[64] = { false };
-  const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 64;
+  const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 8 * 4 + 64;
   auto kern = k_matvec<G, S, H, MODE>;
   if (!attr_set[c->device & 63]) {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -879,10 +881,10 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
 // cg_solve: ref/src/cg_solve.hpp:69-229
 // ---------------------------------------------------------------------------------------------------------
 struct OpTimer {          // CUDA-event pairs per op class, resolved after the solve (no host sync inside)
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[3];
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];     // WAXPY, DOT, MATVEC, MATVECDOT
   cudaStream_t s; int mode;      // 0: none, 1: every op class, 2: MATVEC only (two events per iteration)
   OpTimer(cudaStream_t st, int m) : s(st), mode(m) {}
-  bool on(int cls) const { return mode == 1 || (mode == 2 && cls == MFE_MATVEC); }
+  bool on(int cls) const { return mode == 1 || (mode == 2 && (cls == MFE_MATVEC || cls == MFE_MATVECDOT)); }
   void begin(int cls) { if (!on(cls)) return; cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); ev[cls].push_back({ a, b }); }
   void end(int cls) { if (!on(cls)) return; cudaEventRecord(ev[cls].back().second, s); }
   double total_s(int cls) {
@@ -973,8 +975,12 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
           ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_r, c->d_r, 1, EPI_RR, k, true, hist)) return 1; ot.end(MFE_DOT); // (:158)
           ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_r, ScalarArg{ &sc->beta, 0.0 }, c->d_p, c->d_p, sc, k); ot.end(MFE_WAXPY);  // (:160)
         }
-        ot.begin(MFE_MATVEC); if (launch_matvec(c, c->d_p, c->d_Ap, c->dot_mode != MFE_DOT_SERIAL, sc, k)) return 1; ot.end(MFE_MATVEC);   // (:177)
-        ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_Ap, c->d_p, c->dot_mode != MFE_DOT_SERIAL ? 2 : 0, EPI_PAP, k, true, hist)) return 1; ot.end(MFE_DOT);  // (:179)
+        // MINIFE_FUSED (cg_solve.hpp:172-176): matvec_and_dot = the same SpMV and the same serial-order dot (x[row]*sum
+        // commutes), timed as one MATVECDOT interval; the SpMV always feeds the dot its prediction sums, fused or not
+        const int mv_cls = c->fused ? MFE_MATVECDOT : MFE_MATVEC, pap_cls = c->fused ? MFE_MATVECDOT : MFE_DOT;
+        ot.begin(mv_cls); if (launch_matvec(c, c->d_p, c->d_Ap, c->dot_mode != MFE_DOT_SERIAL, sc, k)) return 1; if (!c->fused) ot.end(mv_cls);   // (:177)
+        if (!c->fused) ot.begin(pap_cls);
+        if (launch_dot(c, n, c->d_Ap, c->d_p, c->dot_mode != MFE_DOT_SERIAL ? 2 : 0, EPI_PAP, k, true, hist)) return 1; ot.end(pap_cls);  // (:179)
       }
       resume_phase = 0;
       ot.begin(MFE_WAXPY);                                                                                               // (:211-212)
@@ -1029,8 +1035,8 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   if (normr) *normr = h.normr;
   if (cg_times) {
     cg_times[MFE_WAXPY] = ot.total_s(MFE_WAXPY); cg_times[MFE_DOT] = ot.total_s(MFE_DOT); cg_times[MFE_MATVEC] = ot.total_s(MFE_MATVEC);
-    cg_times[MFE_MATVECDOT] = 0; cg_times[MFE_TOTAL] = ms * 1e-3;
-  } else { ot.total_s(0); ot.total_s(1); ot.total_s(2); }
+    cg_times[MFE_MATVECDOT] = ot.total_s(MFE_MATVECDOT); cg_times[MFE_TOTAL] = ms * 1e-3;
+  } else { ot.total_s(0); ot.total_s(1); ot.total_s(2); ot.total_s(3); }
   const size_t cap = c->hist_cap, cnt = (size_t)max_iter + 1;
   if (normr_hist) memcpy(normr_hist, hh.data(), cnt * 8);
   if (rtrans_hist) memcpy(rtrans_hist, hh.data() + cap, cnt * 8);
@@ -1039,6 +1045,54 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   CK(cudaGetLastError());
   if (peer_error(c)) return 1;
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// time_kernels: ref/src/time_kernels.hpp:42-134 (MINIFE_KERNELS != 0, driver.hpp:257-270): max_iter x waxpby(1,x,0,x,p),
+// max_iter x matvec(A,p,x), xdotp = sum of max_iter x dot(x,p) -- the same sequences on the device-resident vectors
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int mfe_time_kernels(mfe_ctx *c, double *x_host, int max_iter, double *xdotp, double kern_times[MFE_NUM_TIMERS])
+{
+  if (!c || !c->has_structure) return fail("mfe_time_kernels: no matrix");
+  if (!c->has_local) {
+    fprintf(stderr, "miniFE::time_kernels ERROR, A.has_local_indices is false, needs to be true. This probably means "
+                    "miniFE::make_local_matrix(A) was not called prior to calling miniFE::time_kernels.\n");
+    return fail("mfe_time_kernels: make_local_matrix was not called");
+  }
+  if (max_iter < 0) return fail("mfe_time_kernels: max_iter < 0");
+  CK(cudaSetDevice(c->device));
+  if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
+  const int64_t n = c->nrows;
+  if (x_host) CK(cudaMemcpyAsync(c->d_x, x_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(c->d_p, 0, c->num_cols * 8, c->stream));           // Vector p(0, ncols): zero-filled (time_kernels.hpp:75)
+  double *d_vals = nullptr;
+  if (dev_alloc(&d_vals, std::max(max_iter, 1))) return 1;
+  const ScalarArg one{ nullptr, 1.0 }, zero{ nullptr, 0.0 };
+  cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
+  cudaEventRecord(ev[0], c->stream);
+  for (int i = 0; i < max_iter; ++i) launch_waxpby(c, n, one, c->d_x, zero, c->d_x, c->d_p, nullptr, 0);
+  cudaEventRecord(ev[1], c->stream);
+  for (int i = 0; i < max_iter; ++i) if (launch_matvec(c, c->d_p, c->d_x, false, nullptr, 0)) return 1;
+  cudaEventRecord(ev[2], c->stream);
+  for (int i = 0; i < max_iter; ++i) {
+    if (launch_dot(c, n, c->d_x, c->d_p, 0, EPI_NONE, 0, false, nullptr)) return 1;
+    CK(cudaMemcpyAsync(d_vals + i, c->dot.w.result, 8, cudaMemcpyDeviceToDevice, c->stream));
+  }
+  cudaEventRecord(ev[3], c->stream);
+  std::vector<double> vals(std::max(max_iter, 1));
+  CK(cudaMemcpyAsync(vals.data(), d_vals, 8 * (size_t)std::max(max_iter, 1), cudaMemcpyDeviceToHost, c->stream));
+  if (x_host) CK(cudaMemcpyAsync(x_host, c->d_x, n * 8, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  double acc = 0;                                  // xdotp += dot(x, p), time_kernels.hpp:119-122
+  for (int i = 0; i < max_iter; ++i) acc += vals[i];
+  if (xdotp) *xdotp = acc;
+  float a = 0, b = 0, d = 0;
+  cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&d, ev[2], ev[3]);
+  for (auto &e : ev) cudaEventDestroy(e);
+  cudaFree(d_vals);
+  if (kern_times) { kern_times[MFE_WAXPY] = a * 1e-3; kern_times[MFE_MATVEC] = b * 1e-3; kern_times[MFE_DOT] = d * 1e-3; kern_times[MFE_MATVECDOT] = 0; kern_times[MFE_TOTAL] = 0; }
+  CK(cudaGetLastError());
+  return peer_error(c);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1134,6 +1188,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   }
   if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
   if (!strcmp(name, "pdl")) { c->pdl = value != 0; return 0; }
+  if (!strcmp(name, "fused")) { c->fused = value != 0; return 0; }
   if (!strcmp(name, "peer_timeout_ms")) { if (value < 1) return fail("mfe_set_option: peer_timeout_ms < 1"); c->peer_timeout_ms = value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
@@ -1299,6 +1354,18 @@ extern "C" int mfe_import_csr(mfe_ctx *c, int64_t nrows, int64_t num_cols, const
   CK(cudaStreamSynchronize(c->stream));
   c->has_structure = true; c->has_local = true;
   return 0;
+}
+
+// exact-dot diagnostics (k_dot_walk): out[0..15] = counters, then DOT_STATS_TRACE pairs (slow gaps << 32 | dirty leaves, ns)
+extern "C" int64_t mfe_dot_stats(mfe_ctx *c, uint64_t *out, int64_t cap, int reset)
+{
+  if (!c || !c->dot.w.stats) return -1;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  const int64_t nw = std::min<int64_t>(cap, DOT_STATS_WORDS);
+  if (out && nw > 0 && cudaMemcpy(out, c->dot.w.stats, 8 * nw, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  if (reset) cudaMemset(c->dot.w.stats, 0, 8 * DOT_STATS_WORDS);
+  return DOT_STATS_WORDS;
 }
 
 extern "C" double mfe_phase_ms(const mfe_ctx *c, const char *phase)

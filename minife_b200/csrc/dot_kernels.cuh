@@ -428,6 +428,8 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
   __shared__ DotMap gmaps[DOT_MAX_DIRTY + 1];
   __shared__ double replay_prod[DOT_MAX_DIRTY * DOT_LEAF];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long t_begin = (w.stats && tid == 0) ? global_ns() : 0ULL;
+  int slow_gaps = 0;
   const int D = *w.dirty_count;
   const long long nleaves = ((n + DOT_PIECE - 1) / DOT_PIECE) * 32;     // whole pieces: the maps that exist
   double s = 0.0;
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
     if (tid == 0) {
       for (int g = 0; g <= D; ++g) {
         const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
-        if (lo < hi && !dot_apply(gmaps[g], s)) s = dot_walk_gap_slow(lo, hi, w, x, y, n, s);
+        if (lo < hi && !dot_apply(gmaps[g], s)) { s = dot_walk_gap_slow(lo, hi, w, x, y, n, s); ++slow_gaps; }
         if (g < D) {
           const int64_t b = (int64_t)sorted[g] * DOT_LEAF;
           const int cnt = (int)(b + DOT_LEAF <= n ? DOT_LEAF : n - b);
@@ -495,6 +497,17 @@ __global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const doub
   if (tid == 0) {
     *w.dirty_count = 0;                         // ready for the next dot on this workspace
     if (sc) sc->dot_local = s;
+    if (w.stats) {
+      // diagnostics: [0] dots, [1] sum of dirty leaves, [2] max, [3] whole-vector replays, [4] gaps that took the slow path,
+      // [5] total ns in this kernel, [6] max ns, [7] dot index of the max; then a ring of (dirty leaves, ns) per dot
+      const unsigned long long dt = global_ns() - t_begin, idx = w.stats[0];
+      w.stats[0] = idx + 1; w.stats[1] += (unsigned long long)D; if ((unsigned long long)D > w.stats[2]) w.stats[2] = D;
+      if (D > DOT_MAX_DIRTY) w.stats[3] += 1;
+      w.stats[4] += (unsigned long long)slow_gaps; w.stats[5] += dt;
+      if (dt > w.stats[6]) { w.stats[6] = dt; w.stats[7] = idx; }
+      w.stats[DOT_STATS_HEAD + 2 * (idx % DOT_STATS_TRACE)] = ((unsigned long long)slow_gaps << 32) | (unsigned)D;
+      w.stats[DOT_STATS_HEAD + 2 * (idx % DOT_STATS_TRACE) + 1] = dt;
+    }
   }
   bool ok = true;
   if (pd.nranks > 1) s = peer_dot_allreduce(pd, s, ok);     // rank-ordered global sum over NVLink peer memory

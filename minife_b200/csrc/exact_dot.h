@@ -453,6 +453,7 @@ MFE_HD double dot_replay(const double *x, const double *y, long long begin, long
 // top level: one warp collapses a run with a single coalesced load and an ordered shuffle scan.
 // ---------------------------------------------------------------------------------------------------------
 enum { DOT_LEVELS = 5, DOT_GAP_PIECES = 9 };
+enum { DOT_STATS_HEAD = 16, DOT_STATS_TRACE = 512, DOT_STATS_WORDS = DOT_STATS_HEAD + 2 * DOT_STATS_TRACE };
 MFE_HD int dot_level_size(int level)   // in leaves
 {
   return level == 0 ? 1 : level == 1 ? 32 : level == 2 ? 256 : level == 3 ? 8192 : 262144;
@@ -473,6 +474,7 @@ struct DotWork {
   int *dirty_count;        // 1
   int *dirty_list;         // DOT_MAX_DIRTY leaf indices
   double *result;          // 1
+  unsigned long long *stats; // optional diagnostics (DOT_STATS_WORDS words): see k_dot_walk
 };
 MFE_HD const DotMap *dot_level_maps(const DotWork &w, int level)
 {

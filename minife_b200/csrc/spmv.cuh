@@ -72,6 +72,7 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
   double *racc = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + (size_t)G * S * 8);     // [8] round sums (G == 16)
   int *rcnt = reinterpret_cast<int *>(racc + 8);                                                  // [8] round arrivals
+  volatile int *rtag = rcnt + 8;                                                                  // [8] round each slot collects
   uint64_t pol_stream = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
   const int64_t stride = (int64_t)gridDim.x * G;      // this warp's work items: (blockIdx.x + j * gridDim.x) * G + w
@@ -98,7 +99,7 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x < 8) { racc[threadIdx.x] = 0.0; rcnt[threadIdx.x] = 0; }
+  if (threadIdx.x < 8) { racc[threadIdx.x] = 0.0; rcnt[threadIdx.x] = 0; rtag[threadIdx.x] = (int)threadIdx.x; }
   __syncthreads();
 
   int64_t wi = (int64_t)blockIdx.x * G + w;           // work item
@@ -205,17 +206,24 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
       if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
         if (G == 16 && MODE != MV_LIST) {
           // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
-          // rounds; the warp that completes a round publishes it).  Prediction data: a lagging warp that lets a
-          // slot be reused early can only blur a prediction.
+          // rounds; the warp that completes a round publishes it and hands the slot to round j + 8).  A warp that is
+          // 8 rounds ahead of a straggler waits for the slot (the straggler never waits for a later round, so this
+          // cannot deadlock): the sums must be exact per piece -- a sum that leaks into the wrong piece shifts the
+          // predicted running sum by ~1e-6 relative, the dot then meets binade crossings where it expects none and
+          // falls into its slow path (measured: 50-80 ms per p.Ap dot at 512^3).
           const int slot = (int)(j & 7);
           const int64_t first = t - w;                           // first tile of the round
           const int expect = (int)(ntiles - first < G ? ntiles - first : G);
+          while (rtag[slot] != (int)j) { }
+          __threadfence_block();
           atomicAdd(&racc[slot], prod);
           __threadfence_block();
           if (atomicAdd(&rcnt[slot], 1) == expect - 1) {
             __threadfence_block();
             const double v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(&racc[slot]), 0ULL));
             rcnt[slot] = 0;
+            __threadfence_block();
+            rtag[slot] = (int)j + 8;
             piece_sums[first >> 4] = v;
             atomicAdd(&chunk_sums[first >> 7], v);
           }

@@ -55,6 +55,10 @@ cg_solve(OperatorType& A,
     if (!b.coefs.empty() && mfe_import_vector(e.ctx, "b", &b.coefs[0]) != 0) b200::die("mfe_import_vector");
   }
   e.x_vec = &x;
+#ifdef MINIFE_FUSED
+  // cg_solve.hpp:172-176, 203-206: matvec_and_dot / fused_waxpby -- same arithmetic on the device, reported as MATVECDOT
+  if (mfe_set_option(e.ctx, "fused", 1) != 0) b200::die("mfe_set_option");
+#endif
   std::vector<double> hist(max_iter + 1);
   double times[MFE_NUM_TIMERS] = {0, 0, 0, 0, 0};
   int iters = 0;

@@ -364,3 +364,28 @@ def test_cg_history_bit_exact_with_programmatic_dependent_launch(n, oracle_built
         assert iters == want["num_iters"]
         assert_bits(h["normr"], want["normr"], "normr history (pdl)")
         assert_bits(p.x.coefs, o.x(), "solution x (pdl)")
+
+
+def test_fused_reporting_mode_and_time_kernels(oracle_built, product_lib):
+    """MINIFE_FUSED (ref/src/cg_solve.hpp:172-176): bit-identical history, the SpMV + p.Ap interval lands in cg_times[MATVECDOT];
+    time_kernels (ref/src/time_kernels.hpp:97-124): p = x, x = A p, xdotp = sum of max_iter equal dots -- against the oracle."""
+    n = (20, 30, 40)
+    o = Oracle(*n).setup()
+    want = o.cg_solve(200, EPS)
+    p = Problem(*n).setup()
+    p.mesh.set_option("fused", 1)
+    iters, normr, times, h = mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS, history=True)
+    assert iters == want["num_iters"]
+    assert_bits(h["normr"], want["normr"], "normr history (fused)")
+    assert times[mf.MATVECDOT] > 0 and times[mf.MATVEC] > 0 and times[mf.MATVECDOT] > times[mf.MATVEC]
+    p.mesh.set_option("fused", 0)
+    x0 = np.cos(0.01 * np.arange(p.A.num_rows())) + 1.5
+    p.x.coefs[:] = x0
+    xdotp, kt = mf.time_kernels(p.A, p.b, p.x, mf.matvec_std(), 7)
+    ax = o.matvec(x0)
+    assert_bits(p.x.coefs, ax, "x = A p after time_kernels")
+    d, acc = Oracle.dot(ax, x0), 0.0
+    for _ in range(7):
+        acc += d
+    assert_bits([xdotp], [acc], "xdotp")
+    assert kt[mf.WAXPY] > 0 and kt[mf.MATVEC] > 0 and kt[mf.DOT] > 0
