@@ -146,6 +146,7 @@ struct mfe_ctx {
   int comm_mode = 1;             // 1: NVLink peer stores when available (default), 0: NCCL send/recv + allgather
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
   int pdl = 0;                   // programmatic dependent launch of the CG-loop kernels (launch_cg)
+  int test_no_exchange = 0;      // test hook: skip the halo exchange (the caller supplies the externals), keep the two SpMV passes
   int fused = 0;                 // MINIFE_FUSED reporting: SpMV + dot(Ap,p) are timed as MATVECDOT (cg_solve.hpp:172-176)
   int64_t peer_timeout_ms = 30000;
   std::vector<int> send_dst_offset;
@@ -741,7 +742,7 @@ static int exchange_nccl(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 // first half: peer mode stores my boundary values into the neighbours' halo buffers; NCCL mode does everything
 static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 {
-  if (c->nranks == 1) return 0;
+  if (c->nranks == 1 || c->test_no_exchange) return 0;
   if (!c->comm) return fail("exchange_externals: nranks > 1 but mfe_comm_init was not called");
   if (!use_peer(c)) return exchange_nccl(c, x, gate, k);
   const unsigned long long epoch = ++c->peer.halo_epoch;
@@ -764,7 +765,7 @@ static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 // second half (peer mode): wait for the neighbours' stores of this epoch and fill the external tail of x
 static int exchange_end(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 {
-  if (!use_peer(c)) return 0;
+  if (!use_peer(c) || c->test_no_exchange) return 0;
   const int n_ext = (int)(c->num_cols - c->nrows);
   if (n_ext <= 0) return 0;
   const unsigned long long epoch = c->peer.halo_epoch;
@@ -787,7 +788,7 @@ static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
 static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k)
 {
   if (exchange_begin(c, x, gate, k)) return 1;
-  if (use_peer(c) && c->overlap && c->n_interior > 0 && c->n_boundary > 0) {
+  if ((use_peer(c) || c->test_no_exchange) && c->overlap && c->n_interior > 0 && c->n_boundary > 0) {
     if (launch_matvec_local(c, x, y, with_sums, gate, k, nullptr, 0, c->d_tile_base_flagged)) return 1;   // skips the tiles that need the halo
     if (exchange_end(c, x, gate, k)) return 1;
     return launch_matvec_local(c, x, y, with_sums, gate, k, c->d_tiles_boundary, c->n_boundary);
@@ -1189,6 +1190,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
   if (!strcmp(name, "pdl")) { c->pdl = value != 0; return 0; }
   if (!strcmp(name, "fused")) { c->fused = value != 0; return 0; }
+  if (!strcmp(name, "test_no_exchange")) { c->test_no_exchange = value != 0; return 0; }
   if (!strcmp(name, "peer_timeout_ms")) { if (value < 1) return fail("mfe_set_option: peer_timeout_ms < 1"); c->peer_timeout_ms = value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
@@ -1205,7 +1207,7 @@ extern "C" int mfe_matvec(mfe_ctx *c, double *x_host, double *y_host)
   CK(cudaMemcpyAsync(c->d_tmp1, x_host, c->num_cols * 8, cudaMemcpyHostToDevice, c->stream));
   if (launch_matvec(c, c->d_tmp1, c->d_tmp2, false, nullptr, 0)) return 1;
   CK(cudaMemcpyAsync(y_host, c->d_tmp2, c->nrows * 8, cudaMemcpyDeviceToHost, c->stream));
-  if (c->nranks > 1) CK(cudaMemcpyAsync(x_host + c->nrows, c->d_tmp1 + c->nrows, (c->num_cols - c->nrows) * 8, cudaMemcpyDeviceToHost, c->stream));
+  if (c->nranks > 1 && !c->test_no_exchange) CK(cudaMemcpyAsync(x_host + c->nrows, c->d_tmp1 + c->nrows, (c->num_cols - c->nrows) * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaGetLastError());
   return peer_error(c);

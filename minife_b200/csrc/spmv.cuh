@@ -75,8 +75,21 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   volatile int *rtag = rcnt + 8;                                                                  // [8] round each slot collects
   uint64_t pol_stream = 0;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  const int64_t stride = (int64_t)gridDim.x * G;      // this warp's work items: (blockIdx.x + j * gridDim.x) * G + w
-  auto tile_of = [&](int64_t i) -> int64_t { return MODE == MV_LIST ? (int64_t)tile_list[i] : i; };
+  // Round jj of this CTA covers the work items first .. first + G - 1, first = (blockIdx.x + jj * gridDim.x) * G; warp w
+  // takes item first + w, which is tile first + w (MV_ALL), tile_list[first + w] (MV_LIST), or -- MV_SKIP -- tile
+  // first + (w + jj) % G: the rotation spreads the skipped tiles over the warps (the boundary tiles of an x-split box
+  // recur with period 8 in the tile index, which a fixed warp <-> residue assignment would turn into idle warps).
+  auto item = [&](int64_t jj, int64_t &t) -> bool {
+    const int64_t first = ((int64_t)blockIdx.x + jj * (int64_t)gridDim.x) * G;
+    if (MODE == MV_LIST) {
+      const int64_t i = first + w;
+      if (i >= nwork) return false;
+      t = (int64_t)tile_list[i];
+      return true;
+    }
+    t = first + (MODE == MV_SKIP ? (int64_t)((w + (int)(jj % G)) % G) : (int64_t)w);
+    return t < ntiles;
+  };
   constexpr int64_t SKIP = MODE == MV_SKIP ? MV_SKIP_BIT : 0;
 
   auto issue = [&](int64_t t, int s) -> bool {
@@ -102,10 +115,9 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   if (threadIdx.x < 8) { racc[threadIdx.x] = 0.0; rcnt[threadIdx.x] = 0; rtag[threadIdx.x] = (int)threadIdx.x; }
   __syncthreads();
 
-  int64_t wi = (int64_t)blockIdx.x * G + w;           // work item
   unsigned armed0 = 0;
   if (lane == 0)
-    for (int s = 0; s < S; ++s) { const int64_t ii = wi + s * stride; if (ii < nwork && issue(tile_of(ii), s)) armed0 |= 1u << s; }
+    for (int s = 0; s < S; ++s) { int64_t ti; if (item(s, ti) && issue(ti, s)) armed0 |= 1u << s; }
   asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on x, y, the gate scalars and the sums may be touched
   if (cg_gate_closed(gate, k)) {                        // iteration switched off: let the copies in flight land, then leave
     if (lane == 0)
@@ -117,27 +129,31 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
   // software-pipelined row offsets: (o0,o1) of this lane's row in the NEXT tile are loaded one tile ahead
   uint32_t o0n = 0, o1n = 0; int64_t tb0n = 0, tb1n = 0;
   int64_t tnext = 0;
-  if (wi < nwork) {
-    tnext = tile_of(wi);
+  bool vnext = item(0, tnext);
+  if (vnext) {
     const int64_t r = tnext * TR + lane;
     if (r < nrows) { o0n = roff[r]; o1n = roff[r + 1]; }
     tb0n = tile_base[tnext]; tb1n = tile_base[tnext + 1];
   }
-  for (int64_t j = 0; wi < nwork; ++j, wi += stride) {
+  // a warp without an item in round j has none in any later round (only the last round of the CTA can be partial,
+  // and in MV_SKIP the warp may still own a tile of it -- item() decides)
+  for (int64_t j = 0; ((int64_t)blockIdx.x + j * (int64_t)gridDim.x) * G < nwork; ++j) {
     const int s = (int)(j % S);
     const uint32_t parity = (phase_bits >> s) & 1u;
+    const bool valid = vnext;
     const int64_t t = tnext;
     const int64_t r = t * TR + lane;
     const uint32_t o0 = o0n, o1 = o1n;
     const bool skipped = (tb0n & SKIP) != 0;
     const int64_t tb0 = tb0n & ~SKIP, tb1 = tb1n & ~SKIP;
-    if (wi + stride < nwork) {
-      tnext = tile_of(wi + stride);
+    vnext = item(j + 1, tnext);
+    if (vnext) {
       const int64_t rn = tnext * TR + lane;
       o0n = 0; o1n = 0;
       if (rn < nrows) { o0n = roff[rn]; o1n = roff[rn + 1]; }
       tb0n = tile_base[tnext]; tb1n = tile_base[tnext + 1];
     }
+    if (!valid) continue;
     const int64_t a0 = tb0 & ~3LL;
     int64_t a1 = (tb1 + 3) & ~3LL;
     if (a1 > nnz_padded) a1 = nnz_padded;
@@ -201,8 +217,8 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     }
     __syncwarp();                     // every lane is done with stage s -> it can be refilled
     if (lane == 0) {
-      const int64_t i2 = wi + (int64_t)S * stride;
-      if (i2 < nwork) issue(tile_of(i2), s);
+      int64_t t2;
+      if (item(j + S, t2)) issue(t2, s);
       if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
         if (G == 16 && MODE != MV_LIST) {
           // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
@@ -212,7 +228,7 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
           // predicted running sum by ~1e-6 relative, the dot then meets binade crossings where it expects none and
           // falls into its slow path (measured: 50-80 ms per p.Ap dot at 512^3).
           const int slot = (int)(j & 7);
-          const int64_t first = t - w;                           // first tile of the round
+          const int64_t first = ((int64_t)blockIdx.x + j * (int64_t)gridDim.x) * G;   // first tile of the round
           const int expect = (int)(ntiles - first < G ? ntiles - first : G);
           while (rtag[slot] != (int)j) { }
           __threadfence_block();

@@ -389,3 +389,27 @@ def test_fused_reporting_mode_and_time_kernels(oracle_built, product_lib):
         acc += d
     assert_bits([xdotp], [acc], "xdotp")
     assert kt[mf.WAXPY] > 0 and kt[mf.MATVEC] > 0 and kt[mf.DOT] > 0
+
+
+@pytest.mark.parametrize("n,npr", [((8, 8, 8), 8), ((6, 6, 6), 4), ((5, 3, 7), 3), ((40, 24, 24), 2), ((70, 40, 36), 8), ((33, 80, 17), 4)])
+def test_two_pass_matvec_of_every_rank_bit_exact(n, npr, oracle_built, product_lib):
+    """The overlapped SpMV of a multi-rank run -- interior pass over the flagged tile table (boundary tiles skipped, warps
+    rotated), then the listed boundary tiles -- on every rank's matrix, with the halo supplied by the caller (test hook
+    test_no_exchange) instead of the neighbours: y must equal the oracle's matvec of that rank bit for bit, in a single
+    pass and in two passes, and so must the CG-loop variant that accumulates the p.Ap prediction sums."""
+    o = Oracle(*n, npr).setup()
+    rng = np.random.default_rng(3)
+    for r in range(npr):
+        p = Problem(*n, nranks=npr, rank=r).setup()
+        ncols, nrows = p.A.num_cols, p.A.num_rows()
+        x = rng.standard_normal(ncols)
+        want = o.matvec(x, r)
+        p.mesh.set_option("test_no_exchange", 1)
+        for overlap in (0, 1):
+            p.mesh.set_option("overlap", overlap)
+            for cfg in (0, 2, 4):
+                p.mesh.set_option("matvec_config", cfg)
+                y = np.zeros(nrows)
+                mf.matvec(p.A, x.copy(), y)
+                assert_bits(y, want, "rank %d overlap %d cfg %d" % (r, overlap, cfg))
+        p.mesh.close()
