@@ -88,7 +88,7 @@ def test_minife_fused_build_reproduces_reference(args):
         assert float(grab(yo, "MATVECDOT Time")) > 0.0
         res_o = re.findall(r"(Initial Residual = \S+|Iteration = \d+\s+Residual = \S+)", so)
         res_r = re.findall(r"(Initial Residual = \S+|Iteration = \d+\s+Residual = \S+)", sr)
-        assert res_o == res_r and len(res_o) >= 3
+        assert res_o == res_r and len(res_o) >= 2
 
 
 @pytest.mark.skipif(not os.path.exists(OURS_KERNELS), reason="MINIFE_KERNELS drop-in binary not built")
