@@ -117,7 +117,11 @@ static void build_bc_sets(mfo_world *w, int rank)
   R->nbc[1] = sort_unique(s1, n1); R->bc[1] = s1;
 }
 
-mfo_world *mfo_world_create(int nx, int ny, int nz, int np)
+mfo_world *mfo_world_create(int nx, int ny, int nz, int np) { return mfo_world_create_boxes(nx, ny, nz, np, NULL); }
+
+/* boxes6np == NULL: box_partition (ref/src/main.cpp:112); otherwise the given element boxes, e.g. the ones
+ * add_imbalance (ref/utils/imbalance.hpp:167-293, called at ref/src/driver.hpp:137-139) leaves on the ranks */
+mfo_world *mfo_world_create_boxes(int nx, int ny, int nz, int np, const int *boxes6np)
 {
   mfo_world *w = (mfo_world *)calloc(1, sizeof *w);
   int *boxes = (int *)malloc(sizeof(int) * 6 * np), p, a, off = 0;
@@ -125,7 +129,8 @@ mfo_world *mfo_world_create(int nx, int ny, int nz, int np)
   w->gnx = nx + 1; w->gny = ny + 1; w->gnz = nz + 1;
   w->global_nrows = w->gnx * w->gny * w->gnz;
   w->r = (mfo_rank *)calloc(np, sizeof(mfo_rank));
-  mfo_box_partition(nx, ny, nz, np, boxes);
+  if (boxes6np) memcpy(boxes, boxes6np, sizeof(int) * 6 * np);
+  else mfo_box_partition(nx, ny, nz, np, boxes);
   {
     int g[3]; g[0] = nx; g[1] = ny; g[2] = nz;
     for (p = 0; p < np; ++p) {

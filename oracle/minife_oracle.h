@@ -34,6 +34,8 @@ void mfo_gradient_values(double *out192);
 void mfo_element(int nx, int ny, int nz, int elemID, int *node_ids8, double *coords24, double *K36, double *f8);
 
 mfo_world *mfo_world_create(int nx, int ny, int nz, int nranks);
+/* same with caller-supplied element boxes (6 ints per rank), e.g. after add_imbalance (ref/utils/imbalance.hpp:167-293) */
+mfo_world *mfo_world_create_boxes(int nx, int ny, int nz, int nranks, const int *boxes6n);
 void mfo_world_destroy(mfo_world *w);
 
 /* phases (all ranks), in the order of ref/src/driver.hpp:159-289 */

@@ -41,6 +41,10 @@
 #include <Vector_functions.hpp>
 #include <cg_solve.hpp>
 #include <verify_solution.hpp>
+#ifdef REF_DUMP_MAIN
+#include <YAML_Doc.hpp>
+#include <imbalance.hpp>
+#endif
 
 typedef miniFE::CSRMatrix<double, int, int> RefMatrix;
 typedef miniFE::Vector<double, int, int> RefVector;
@@ -343,7 +347,8 @@ void ref_box_partition(int nx, int ny, int nz, int np, int* out6np)
 
 #ifdef REF_DUMP_MAIN
 // ---------------------------------------------------------------------------
-// Multi-rank dump process: ref_dump_mpi.x nx ny nz outdir [cg_max_iter]
+// Multi-rank dump process: ref_dump_mpi.x nx ny nz outdir [cg_max_iter [load_imbalance_percent]]
+// (load_imbalance > 0: the boxes are changed by add_imbalance exactly as ref/src/driver.hpp:137-139 does)
 // Runs the reference pipeline on this rank (MPI via oracle/mpi_shim) and writes
 //   <outdir>/<name>.<np>.<rank>.{i32,f64}
 // ---------------------------------------------------------------------------
@@ -371,8 +376,16 @@ int main(int argc, char** argv)
   int nx = std::atoi(argv[1]), ny = std::atoi(argv[2]), nz = std::atoi(argv[3]);
   std::string dir = argv[4];
   int max_iter = argc > 5 ? std::atoi(argv[5]) : 200;
+  float load_imbalance = argc > 6 ? (float)std::atof(argv[6]) : 0.0f;
 
   RefProblem* P = make_problem(nx, ny, nz, numprocs, myproc);
+  if (load_imbalance > 0) {      // ref/src/driver.hpp:137-139, then the mesh is (re)built from the changed box
+    YAML_Doc ydoc("miniFE", "dump");
+    { CoutCapture quiet; miniFE::add_imbalance<int>(P->global_box, P->my_box, load_imbalance, ydoc); }
+    delete P->mesh;
+    CoutCapture quiet;
+    P->mesh = new RefMesh(P->global_box, P->my_box);
+  }
   { CoutCapture quiet; miniFE::generate_matrix_structure(*P->mesh, P->A); }
   make_vectors(P);
   dumpv(dir, "rows", numprocs, myproc, "i32", P->A.rows);

@@ -46,12 +46,16 @@ static void rcb(int ip, int up, int axis, const int *box, int *out)
 
 extern "C" {
 
-void *hs_create(int nx, int ny, int nz, int np, int rank)
+void *hs_create_boxes(int nx, int ny, int nz, int np, int rank, const int *boxes6np);
+void *hs_create(int nx, int ny, int nz, int np, int rank) { return hs_create_boxes(nx, ny, nz, np, rank, nullptr); }
+// boxes6np == nullptr: box_partition; otherwise caller-supplied element boxes (e.g. after add_imbalance)
+void *hs_create_boxes(int nx, int ny, int nz, int np, int rank, const int *boxes6np)
 {
   Harness *h = new Harness;
   std::vector<int> all(6 * np);
   const int g[6] = { 0, nx, 0, ny, 0, nz };
-  rcb(0, np, 2, g, all.data());
+  if (boxes6np) all.assign(boxes6np, boxes6np + 6 * np);
+  else rcb(0, np, 2, g, all.data());
   MeshDesc &m = h->m;
   m.nx = nx; m.ny = ny; m.nz = nz; m.gnx = nx + 1; m.gny = ny + 1; m.gnz = nz + 1;
   m.nranks = np; m.rank = rank;

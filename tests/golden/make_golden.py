@@ -46,9 +46,11 @@ def history_case(n):
     return dict(n=np.array([n] * 3), num_iters=h["num_iters"], final_normr=h["final_normr"], normr=h["normr"], pap=h["pap"], alpha=h["alpha"], crc_x=crc(r.x()))
 
 
-def mpi_case(n, npr):
-    d = ref_dump_mpi(*n, npr)
+def mpi_case(n, npr, imbalance=0):
+    d = ref_dump_mpi(*n, npr, imbalance=imbalance)
     out = dict(n=np.array(n), np=npr)
+    if imbalance:
+        out["imbalance"] = imbalance
     for r in range(npr):
         for k in ("box", "rows", "row_offsets", "cols_global", "cols_local", "external_index", "external_local_index", "elements_to_send",
                   "neighbors", "recv_length", "send_length", "num_cols"):
@@ -68,6 +70,9 @@ def main():
         np.savez_compressed(os.path.join(HERE, "history_%d.npz" % n), **history_case(n))
     for n, npr in (((2, 2, 2), 2), ((2, 2, 2), 8), ((8, 8, 8), 8), ((6, 6, 6), 4), ((5, 3, 7), 3)):
         np.savez_compressed(os.path.join(HERE, "mpi_%dx%dx%d_np%d.npz" % (n + (npr,))), **mpi_case(n, npr))
+    # boxes changed by the reference's own add_imbalance (load_imbalance percent), ref/src/driver.hpp:137-139
+    for n, npr, imb in (((12, 12, 12), 8, 30), ((10, 9, 8), 4, 60), ((9, 14, 11), 6, 40)):
+        np.savez_compressed(os.path.join(HERE, "mpi_%dx%dx%d_np%d_imb%d.npz" % (n + (npr, imb))), **mpi_case(n, npr, imb))
     if args.big:
         for n in (128, 256):
             np.savez_compressed(os.path.join(HERE, "history_%d.npz" % n), **history_case(n))

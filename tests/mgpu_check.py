@@ -2,7 +2,7 @@
 """Multi-GPU parity check, one rank per GPU (run under torch.distributed.run; needs N GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tests/mgpu_check.py [--sizes 8x8x8,20x30x40,64x64x64]
+        tests/mgpu_check.py [--sizes 8x8x8,20x30x40,64x64x64,tests/golden/mpi_12x12x12_np8_imb30.npz]
 
 Every rank builds its share with minife_b200 (halo exchange + rank-ordered dot all-reduce, over NVLink peer stores with
 and without SpMV overlap and over NCCL) and compares with the
@@ -44,11 +44,20 @@ def main():
             print("[rank %d] MISMATCH: %s" % (rank, what), flush=True)
 
     for size, mode in [(s_, m_) for s_ in args.sizes.split(",") for m_ in args.modes.split(",")]:
-        n = tuple(int(v) for v in size.split("x"))
+        gold_boxes = None
+        if size.endswith(".npz"):      # a golden file of the reference run with add_imbalance: use ITS boxes (np must match)
+            g = np.load(size)
+            if int(g["np"]) != world:
+                continue
+            n = tuple(int(v) for v in g["n"])
+            gold_boxes = np.stack([g["box_%d" % r] for r in range(world)])
+            size = os.path.basename(size)[:-4]
+        else:
+            n = tuple(int(v) for v in size.split("x"))
         if min(n) * 1 < 1 or (n[0] * n[1] * n[2]) < world:
             continue
         gbox = mf.Box([0, n[0], 0, n[1], 0, n[2]])
-        boxes = mf.box_partition(0, world, 2, gbox)
+        boxes = mf.box_partition(0, world, 2, gbox) if gold_boxes is None else [mf.Box(b) for b in gold_boxes]
         if any((b.ranges[1] - b.ranges[0]) * (b.ranges[3] - b.ranges[2]) * (b.ranges[5] - b.ranges[4]) == 0 for b in boxes):
             continue      # the reference itself refuses ranks without elements (main.cpp:116-130)
         mesh = mf.simple_mesh_description(gbox, boxes[rank], rank=rank, nranks=world, all_boxes=boxes, device=local)
@@ -66,11 +75,12 @@ def main():
         mf.assemble_FE_data(mesh, A, b)
         mf.impose_dirichlet(0.0, A, b, bc_rows=0); mf.impose_dirichlet(1.0, A, b, bc_rows=1)
         mf.make_local_matrix(A)
-        if n not in oracles:
+        okey = (n, None if gold_boxes is None else gold_boxes.tobytes())
+        if okey not in oracles:
             oracles.clear()
-            oracles[n] = Oracle(*n, world).setup()
-            oracles[n]._cg = oracles[n].cg_solve(200, EPS)
-        o = oracles[n]
+            oracles[okey] = Oracle(*n, world, boxes=gold_boxes).setup()
+            oracles[okey]._cg = oracles[okey].cg_solve(200, EPS)
+        o = oracles[okey]
         rows, ro, cols, coefs = o.csr(rank)
         check(np.array_equal(A.row_offsets, ro) and np.array_equal(A.packed_cols, cols), "%s CSR structure" % size)
         check(np.array_equal(bits(A.packed_coefs), bits(coefs)) and np.array_equal(bits(b.coefs), bits(o.b(rank))), "%s A/b values" % size)

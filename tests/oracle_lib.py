@@ -58,6 +58,8 @@ class Oracle:
             L = C.CDLL(ORACLE_SO)
             L.mfo_world_create.restype = C.c_void_p
             L.mfo_world_create.argtypes = [C.c_int] * 4
+            L.mfo_world_create_boxes.restype = C.c_void_p
+            L.mfo_world_create_boxes.argtypes = [C.c_int] * 4 + [C.c_void_p]
             L.mfo_world_destroy.argtypes = [C.c_void_p]
             for n in ("mfo_generate_matrix_structure", "mfo_assemble_FE_data", "mfo_make_local_matrix"):
                 getattr(L, n).argtypes = [C.c_void_p]
@@ -87,10 +89,15 @@ class Oracle:
             cls._lib = L
         return cls._lib
 
-    def __init__(self, nx, ny, nz, nranks=1):
+    def __init__(self, nx, ny, nz, nranks=1, boxes=None):
+        """boxes: optional (nranks, 6) int array of element boxes (e.g. after the reference's add_imbalance)"""
         self.L = self.lib()
         self.nx, self.ny, self.nz, self.np = nx, ny, nz, nranks
-        self.h = self.L.mfo_world_create(nx, ny, nz, nranks)
+        if boxes is None:
+            self.h = self.L.mfo_world_create(nx, ny, nz, nranks)
+        else:
+            bx = np.ascontiguousarray(boxes, np.int32).reshape(nranks, 6)
+            self.h = self.L.mfo_world_create_boxes(nx, ny, nz, nranks, bx.ctypes.data_as(C.c_void_p))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -339,13 +346,14 @@ _DUMP_INT = ("rows", "row_offsets", "cols_global", "cols_local", "box", "num_col
 _DUMP_F64 = ("coefs_prebc", "b_prebc", "coefs", "b", "normr_hist", "pap_hist", "x")
 
 
-def ref_dump_mpi(nx, ny, nz, nranks, max_iter=200, timeout=600):
-    """Run the unmodified reference on `nranks` ranks (MPI shim) and return {name: [per-rank arrays]}."""
+def ref_dump_mpi(nx, ny, nz, nranks, max_iter=200, timeout=600, imbalance=0):
+    """Run the unmodified reference on `nranks` ranks (MPI shim) and return {name: [per-rank arrays]}.
+    imbalance > 0: the reference's add_imbalance(load_imbalance = imbalance percent) changes the boxes first."""
     sys.path.insert(0, os.path.join(ORACLE_DIR, "mpi_shim"))
     import launch  # noqa
     out = {}
     with tempfile.TemporaryDirectory() as d:
-        rc = launch.launch(nranks, [REF_DUMP, str(nx), str(ny), str(nz), d, str(max_iter)],
+        rc = launch.launch(nranks, [REF_DUMP, str(nx), str(ny), str(nz), d, str(max_iter)] + ([str(imbalance)] if imbalance else []),
                            timeout=timeout, stdout=subprocess.DEVNULL)
         if rc != 0:
             raise RuntimeError("ref_dump_mpi.x failed rc=%d" % rc)

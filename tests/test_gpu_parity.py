@@ -27,9 +27,9 @@ def assert_bits(a, b, what):
 class Problem:
     """One rank of an nx*ny*nz problem on cuda:0 through the reference-shaped API."""
 
-    def __init__(self, nx, ny, nz, nranks=1, rank=0):
+    def __init__(self, nx, ny, nz, nranks=1, rank=0, boxes=None):
         self.gbox = mf.Box([0, nx, 0, ny, 0, nz])
-        self.boxes = mf.box_partition(0, nranks, 2, self.gbox)
+        self.boxes = mf.box_partition(0, nranks, 2, self.gbox) if boxes is None else [mf.Box(b) for b in boxes]
         self.mesh = mf.simple_mesh_description(self.gbox, self.boxes[rank], rank=rank, nranks=nranks, all_boxes=self.boxes)
         self.A = mf.CSRMatrix()
         self.b = None
@@ -412,4 +412,39 @@ def test_two_pass_matvec_of_every_rank_bit_exact(n, npr, oracle_built, product_l
                 y = np.zeros(nrows)
                 mf.matvec(p.A, x.copy(), y)
                 assert_bits(y, want, "rank %d overlap %d cfg %d" % (r, overlap, cfg))
+        p.mesh.close()
+
+
+import glob as _glob
+import os as _os
+_IMB = sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "mpi_*_imb*.npz")))
+
+
+@pytest.mark.parametrize("path", _IMB)
+def test_boxes_changed_by_add_imbalance(path, oracle_built, product_lib):
+    """the reference's add_imbalance (ref/utils/imbalance.hpp:167-293, driver.hpp:137-139) shifts whole box
+    planes, so the ranks no longer form an RCB partition.  The golden files hold what the UNMODIFIED reference computes on
+    such boxes (through the MPI shim); every rank's structure, index maps, values and two-pass SpMV must match."""
+    g = np.load(path)
+    n, npr = tuple(int(v) for v in g["n"]), int(g["np"])
+    boxes = np.stack([g["box_%d" % r] for r in range(npr)])
+    o = Oracle(*n, npr, boxes=boxes).setup()
+    rng = np.random.default_rng(7)
+    for r in range(npr):
+        p = Problem(*n, nranks=npr, rank=r, boxes=boxes).structure()
+        assert np.array_equal(p.A.rows, g["rows_%d" % r]) and np.array_equal(p.A.row_offsets, g["row_offsets_%d" % r])
+        assert np.array_equal(p.A.packed_cols, g["cols_global_%d" % r])
+        p.assemble().bc().local()
+        assert np.array_equal(p.A.packed_cols, g["cols_local_%d" % r]) and p.A.num_cols == int(g["num_cols_%d" % r][0])
+        for m in ("external_index", "external_local_index", "elements_to_send", "neighbors", "recv_length", "send_length"):
+            assert np.array_equal(getattr(p.A, m), g["%s_%d" % (m, r)]), (r, m)
+        assert_bits(p.A.packed_coefs, o.csr(r)[3], "rank %d A" % r)
+        assert_bits(p.b.coefs, o.b(r), "rank %d b" % r)
+        x = rng.standard_normal(p.A.num_cols)
+        p.mesh.set_option("test_no_exchange", 1)
+        for overlap in (0, 1):
+            p.mesh.set_option("overlap", overlap)
+            y = np.zeros(p.A.num_rows())
+            mf.matvec(p.A, x.copy(), y)
+            assert_bits(y, o.matvec(x, r), "rank %d matvec overlap %d" % (r, overlap))
         p.mesh.close()

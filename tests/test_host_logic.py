@@ -5,6 +5,7 @@ exact_dot.h, halo_maps.h) and executes them thread by thread; this checks them a
 analytic structure, element arithmetic order, row-owner gather, Dirichlet rows, halo index maps without messages,
 and the order-reproducing dot."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -73,10 +74,20 @@ CASES = [((4, 4, 4), 1, 100), ((5, 3, 7), 1, 2), ((2, 2, 2), 8, 1), ((8, 8, 8), 
          ((12, 10, 9), 5, 4), ((16, 16, 16), 2, 5), ((3, 9, 4), 7, 2), ((20, 6, 11), 6, 3), ((1, 1, 2), 1, 1), ((1, 1, 2), 2, 1)]
 
 
-@pytest.mark.parametrize("n,npr,planes", CASES)
+IMBALANCED = sorted(__import__("glob").glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpi_*_imb*.npz")))
+
+
+@pytest.mark.parametrize("n,npr,planes", CASES + [(p, 0, 3) for p in IMBALANCED])
 def test_structure_assembly_dirichlet_maps(H, oracle_built, n, npr, planes):
-    o = Oracle(*n, npr); o.generate_matrix_structure()
-    hs = [H.hs_create(*n, npr, r) for r in range(npr)]
+    boxes = None
+    if isinstance(n, str):       # boxes left by the reference's add_imbalance (golden file): not an RCB partition
+        g = np.load(n)
+        n, npr = tuple(int(v) for v in g["n"]), int(g["np"])
+        boxes = np.ascontiguousarray(np.stack([g["box_%d" % r] for r in range(npr)]), np.int32)
+        H.hs_create_boxes.restype = C.c_void_p
+        H.hs_create_boxes.argtypes = [C.c_int] * 5 + [C.c_void_p]
+    o = Oracle(*n, npr, boxes=boxes); o.generate_matrix_structure()
+    hs = [H.hs_create(*n, npr, r) if boxes is None else H.hs_create_boxes(*n, npr, r, boxes.ctypes.data_as(C.c_void_p)) for r in range(npr)]
     try:
         for r, h in enumerate(hs):
             H.hs_structure(h); rows, ro, cols, co, b = get(H, h); R = o.csr(r)

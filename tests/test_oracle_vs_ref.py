@@ -75,7 +75,8 @@ def test_reference_known_answers():
 def test_multirank_golden(path, oracle_built):
     g = np.load(path)
     n, npr = tuple(int(v) for v in g["n"]), int(g["np"])
-    o = Oracle(*n, npr)
+    # *_imb*.npz: the boxes are the ones the reference's add_imbalance left on the ranks (not an RCB partition)
+    o = Oracle(*n, npr, boxes=np.stack([g["box_%d" % r] for r in range(npr)]) if "imbalance" in g else None)
     o.generate_matrix_structure()
     for r in range(npr):
         rows, ro, cols, _ = o.csr(r)
