@@ -147,6 +147,7 @@ struct mfe_ctx {
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
   int pdl = 0;                   // programmatic dependent launch of the CG-loop kernels (launch_cg)
   int test_no_exchange = 0;      // test hook: skip the halo exchange (the caller supplies the externals), keep the two SpMV passes
+  int ell_width = 0;             // > 0: the matrix stands for the reference's ELLMatrix of that row width (padding terms in the SpMV)
   int fused = 0;                 // MINIFE_FUSED reporting: SpMV + dot(Ap,p) are timed as MATVECDOT (cg_solve.hpp:172-176)
   int64_t peer_timeout_ms = 30000;
   std::vector<int> send_dst_offset;
@@ -695,7 +696,7 @@ static int launch_matvec_mode(mfe_ctx *c, const double *x, double *y, bool with_
   if (nwork <= 0) return 0;
   const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (nwork + G - 1) / G));
   CK(launch_cg(c, kern, dim3(grid), dim3(32 * G), smem, c->d_coefs, c->d_cols, c->d_roff, tile_base ? tile_base : c->d_tile_base, x, y, c->nrows, c->ntiles,
-               c->nnz_padded, 0, with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork));
+               c->nnz_padded, 0, with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork, c->ell_width));
   return 0;
 }
 
@@ -1191,6 +1192,11 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   if (!strcmp(name, "pdl")) { c->pdl = value != 0; return 0; }
   if (!strcmp(name, "fused")) { c->fused = value != 0; return 0; }
   if (!strcmp(name, "test_no_exchange")) { c->test_no_exchange = value != 0; return 0; }
+  if (!strcmp(name, "ell_width")) {          // ref/src/ELLMatrix.hpp: 0 = CSR semantics, 27 = the width generate_matrix_structure reserves
+    if (value < 0 || value > 64) return fail("mfe_set_option: ell_width must be in [0,64]");
+    c->ell_width = (int)value;
+    return 0;
+  }
   if (!strcmp(name, "peer_timeout_ms")) { if (value < 1) return fail("mfe_set_option: peer_timeout_ms < 1"); c->peer_timeout_ms = value; return 0; }
   return fail("mfe_set_option: unknown option '%s'", name);
 }
@@ -1402,7 +1408,7 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
   auto body = [&](int rep) -> int {
     if (!strcmp(what, "matvec")) return launch_matvec_local(c, c->d_p, c->d_Ap, false, nullptr, 0);
     if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, c->d_p, c->d_Ap, true, nullptr, 0);
-    if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n); c->launches++; return 0; }
+    if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n, c->ell_width); c->launches++; return 0; }
     if (!strcmp(what, "stream_probe")) {
       constexpr int PG = 16, PS = 1;
       const size_t smem = (size_t)PG * PS * MatvecCfg::SLOT_BYTES + (size_t)PG * PS * 8 + 64;

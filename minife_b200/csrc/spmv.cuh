@@ -52,8 +52,12 @@ __global__ void __launch_bounds__(32 * G, 1)
 k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
          const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
          int64_t ntiles, int64_t nnz_padded, int zmask, double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
-         const CgScalars *gate, int k, const int *__restrict__ tile_list, int64_t nwork)
+         const CgScalars *gate, int k, const int *__restrict__ tile_list, int64_t nwork, int ell_width)
 {
+  // ell_width > 0: the matrix stands for the reference's ELLMatrix (ref/src/ELLMatrix.hpp), whose matvec
+  // (SparseMatrix_functions.hpp:580-613) walks ell_width entries in every row: a row with fewer real entries ends with
+  // padding entries (coef 0.0, col 0), i.e. with (ell_width - len) additions of 0.0 * x[0].  Reproduced literally (they
+  // decide the sign of a zero result and propagate a non-finite x[0]), on the ragged path only.
   // Programmatic dependent launch: everything up to griddepcontrol.wait below touches only the matrix (static
   // during a solve), so the first tiles are already streaming in while the previous kernel (the p update) drains.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -204,10 +208,18 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
 #pragma unroll
           for (int u = 0; u < B; ++u) dadd_if(sum, __dmul_rn(cv[u], xv[u]), i0 + u, len);
         }
+        if (len < ell_width) {
+          const double pad = __dmul_rn(0.0, __ldg(x));
+          for (int u = len; u < ell_width; ++u) sum = __dadd_rn(sum, pad);
+        }
       }
     } else if (live) {
       const int64_t b0 = tb0 + (int64_t)(uint32_t)(o0 - (uint32_t)tb0);
       for (int64_t i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[b0 + i], __ldg(x + cols[b0 + i])));
+      if (len < ell_width) {
+        const double pad = __dmul_rn(0.0, __ldg(x));
+        for (int u = len; u < ell_width; ++u) sum = __dadd_rn(sum, pad);
+      }
     }
     double prod = 0.0;
     if (live) { y[r] = sum; prod = xr * sum; }
@@ -305,7 +317,7 @@ k_stream_probe(const double *__restrict__ coefs, const int *__restrict__ cols, c
 // plain thread-per-row CSR SpMV in the reference order (validation twin of k_matvec)
 __global__ void k_matvec_simple(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
                                 const int64_t *__restrict__ tile_base, int tr, const double *__restrict__ x, double *__restrict__ y,
-                                int64_t nrows)
+                                int64_t nrows, int ell_width = 0)
 {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
@@ -314,6 +326,7 @@ __global__ void k_matvec_simple(const double *__restrict__ coefs, const int *__r
   const int len = (int)(uint32_t)(roff[r + 1] - roff[r]);
   double sum = 0.0;
   for (int i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[off + i], __ldg(x + cols[off + i])));
+  for (int i = len; i < ell_width; ++i) sum = __dadd_rn(sum, __dmul_rn(0.0, __ldg(x)));
   y[r] = sum;
 }
 

@@ -42,7 +42,7 @@ void write_matrix(const std::string& filename,
   std::string full_name = osstr.str();
   std::ofstream ofs(full_name.c_str());
   size_t nrows_sz = mat.rows.size();
-  size_t nnz_sz = nnz;
+  size_t nnz_sz = mat.num_nonzeros();      // CSRMatrix: row_offsets[nrows]; ELLMatrix: rows * num_cols_per_row (padding counted)
   for(int p=0; p<numprocs; ++p) {
     if (p == myproc) {
       if (p == 0) {
