@@ -448,3 +448,39 @@ def test_boxes_changed_by_add_imbalance(path, oracle_built, product_lib):
             mf.matvec(p.A, x.copy(), y)
             assert_bits(y, o.matvec(x, r), "rank %d matvec overlap %d" % (r, overlap))
         p.mesh.close()
+
+
+def test_pll_matvec_known_answers(product_lib):
+    """The hand matrices of ref/basic/utest_cases.hpp:518-617 (pll_matvec2: 4x4 over 2 ranks) and 619-735 (pll_matvec3: 6x6
+    over 3 ranks) with their exact answers -- API-independent data.  Every rank's rows are imported in
+    local-index form (owned columns first, externals appended in first-encounter order, make_local_matrix.hpp:87-180) and
+    multiplied with the vector the halo exchange would have produced."""
+    cases = [
+        (np.array([[1, 1, 0, 0], [2, 1, -1, 1], [0, -2, 1, 0], [0, 2, 0, 1]], float), [1, 2, 3, 4], [3, 5, -1, 8], 2),
+        (np.array([[1, 0, 0, -1, 0, 0], [0, 1, 0, 0, 0, -1], [2, 0, 1, 0, -1, 0], [0, 0, 0, 1, 0, 0], [0, 2, 0, 0, 1, 0], [0, 0, 0, 2, 0, 1]], float),
+         [1, 2, 3, 4, 5, 6], [-3, -4, 0, 4, 9, 14], 3),
+    ]
+    for A, x, want, nranks in cases:
+        x, want = np.array(x, float), np.array(want, float)
+        per = len(x) // nranks
+        for r in range(nranks):
+            lo, hi = r * per, (r + 1) * per
+            ext = []                                    # global ids of the externals, first-encounter order
+            ro, cols, coefs = [0], [], []
+            for i in range(lo, hi):
+                for j in np.nonzero(A[i])[0]:
+                    if lo <= j < hi:
+                        cols.append(j - lo)
+                    else:
+                        if j not in ext:
+                            ext.append(int(j))
+                        cols.append(per + ext.index(int(j)))
+                    coefs.append(A[i, j])
+                ro.append(len(cols))
+            xl = np.concatenate([x[lo:hi], x[ext]]) if ext else x[lo:hi].copy()
+            p = Problem(4, 4, 4)
+            mf.lib().mfe_import_csr(p.mesh._h, per, len(xl), np.array(ro, np.int32), np.array(cols, np.int32), np.array(coefs, float))
+            y = np.zeros(per)
+            assert mf.lib().mfe_matvec(p.mesh._h, np.ascontiguousarray(xl), y) == 0, mf.lib().mfe_last_error()
+            assert_bits(y, want[lo:hi], "pll_matvec%d rank %d" % (nranks, r))
+            p.mesh.close()
