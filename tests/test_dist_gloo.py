@@ -21,18 +21,23 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, n, so, q):
+def _worker(rank, world, port, n, so, q, golden=None):
     try:
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
         dist.init_process_group("gloo", rank=rank, world_size=world)
         from oracle_lib import Oracle
         H = C.CDLL(so)
         H.hs_create.restype = C.c_void_p; H.hs_create.argtypes = [C.c_int] * 5
+        H.hs_create_boxes.restype = C.c_void_p; H.hs_create_boxes.argtypes = [C.c_int] * 5 + [C.c_void_p]
+        boxes = None
+        if golden:               # boxes left by the reference's add_imbalance (not an RCB partition)
+            g = np.load(golden)
+            boxes = np.ascontiguousarray(np.stack([g["box_%d" % r] for r in range(world)]), np.int32)
         H.hs_structure.argtypes = [C.c_void_p]; H.hs_make_local.argtypes = [C.c_void_p]
         H.hs_nrows.restype = C.c_longlong; H.hs_nrows.argtypes = [C.c_void_p]
         H.hs_num_cols.restype = C.c_longlong; H.hs_num_cols.argtypes = [C.c_void_p]
         H.hs_get_map.restype = C.c_longlong; H.hs_get_map.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
-        h = H.hs_create(*n, world, rank)
+        h = H.hs_create(*n, world, rank) if boxes is None else H.hs_create_boxes(*n, world, rank, boxes.ctypes.data_as(C.c_void_p))
         H.hs_structure(h); H.hs_make_local(h)
 
         def gm(name):
@@ -42,7 +47,7 @@ def _worker(rank, world, port, n, so, q):
             return a
         nrows, ncols = H.hs_nrows(h), H.hs_num_cols(h)
         nb, rl, sl, ets = gm("neighbors"), gm("recv_length"), gm("send_length"), gm("elements_to_send")
-        o = Oracle(*n, world).setup()
+        o = Oracle(*n, world, boxes=boxes).setup()
         first = o.first_row(rank)
         x = np.zeros(ncols); x[:nrows] = np.cos(0.1 * (first + np.arange(nrows))) + 2.0
         # exchange_externals (ref/src/exchange_externals.hpp:90-153) with the product's lists
@@ -96,13 +101,14 @@ def _worker(rank, world, port, n, so, q):
         q.put((rank, "error: %r" % (e,)))
 
 
-@pytest.mark.parametrize("n,world", [((8, 8, 8), 2), ((6, 5, 7), 2), ((8, 8, 8), 4)])
-def test_halo_exchange_and_ordered_dot_over_gloo(harness, oracle_built, n, world):
+@pytest.mark.parametrize("n,world,golden", [((8, 8, 8), 2, None), ((6, 5, 7), 2, None), ((8, 8, 8), 4, None),
+                                            ((10, 9, 8), 4, os.path.join(HERE, "golden", "mpi_10x9x8_np4_imb60.npz"))])
+def test_halo_exchange_and_ordered_dot_over_gloo(harness, oracle_built, n, world, golden):
     so = os.path.join(HERE, "libcpu_harness.so")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, so, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, so, q, golden)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in range(world)]
