@@ -171,3 +171,36 @@ def test_exact_dot_on_cg_vectors(H, oracle_built):
         rn = Oracle.waxpby(1.0, r, -alpha, Ap)
         beta = Oracle.dot(rn, rn) / Oracle.dot(r, r)
         p = Oracle.waxpby(1.0, rn, beta, p); r = rn
+
+
+def test_exact_dot_randomised_stress(H):
+    """Randomised classes the CG never produces but a caller of mfe_dot may: wide dynamic range, sign flips, sums that
+    return to (or sit exactly on) a power of two, runs of zeros between exact values, sparse spikes."""
+    rng = np.random.default_rng(20261017)
+    trials = 0
+    for n in (17, 513, 4097, 33000, 131072 + 5):
+        for kind in range(8):
+            if kind == 0:      # wide dynamic range, positive
+                x = rng.random(n) * 10.0 ** rng.integers(-30, 30, n); y = x
+            elif kind == 1:    # random signs, wide range
+                x = rng.standard_normal(n) * 10.0 ** rng.integers(-12, 12, n); y = rng.standard_normal(n)
+            elif kind == 2:    # exact small integers: sums hit powers of two exactly, with zero runs in between
+                x = (rng.random(n) < 0.02).astype(np.float64); y = x
+            elif kind == 3:    # cancellation back to exactly zero and up again
+                x = np.tile([1.0, -1.0, 0.5, -0.5], n // 4 + 1)[:n]; y = np.ones(n)
+            elif kind == 4:    # halves and quarters: every addition is an exact tie candidate
+                x = rng.integers(-3, 4, n) * 0.25; y = np.ones(n) * (1.0 + 2.0 ** -52)
+            elif kind == 5:    # slow drift around a binade boundary
+                x = np.full(n, 2.0 ** -30); x[0] = 1.0 - 2.0 ** -20; y = np.where(rng.random(n) < 0.5, 1.0, -1.0); y[0] = 1.0
+            elif kind == 6:    # sparse spikes over a tiny background
+                x = rng.random(n) * 1e-12; x[rng.integers(0, n, 5)] = 1e6; y = x
+            else:              # negative running sum
+                x = -np.abs(rng.standard_normal(n)); y = np.abs(rng.standard_normal(n)) + 0.01
+            x, y = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)
+            st = np.zeros(4, np.int64)
+            got = H.hs_exact_dot(n, x, y, P(st))
+            want = H.hs_serial_dot(n, x, y)
+            assert got == want or (np.isnan(got) and np.isnan(want)), (n, kind, got, want)
+            assert st[3] == 0, (n, kind, "fp and integer map formulations disagree")
+            trials += 1
+    assert trials == 40
