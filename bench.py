@@ -170,7 +170,9 @@ def reference_arm(args, rank):
         "OpenMP (openmp/src, unmodified)" if last["kind"] == "reference" else "C port", sample, dims[0], dims[1], dims[2], last["cores"])
     line = {"impl": "reference", "metric": "cg_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "miniFE %dx%dx%d hex8 Poisson, 200-iteration unpreconditioned CG" % tuple(dims), "sample": desc},
+            "config": {"workload": "miniFE %dx%dx%d hex8 Poisson (%s), assembled on device, 200-iteration unpreconditioned CG" % (
+                           dims[0], dims[1], dims[2], "strong scaling: fixed global mesh" if args.strong else "%d^3 elements per GPU" % args.nx),
+                       "sample": desc, "parallelism": "reference OpenMP build on %d host threads (no GPU)" % last["cores"], "flop_model": "ref/src/driver.hpp:322-341"},
             "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": last["cores"], "kind": last["kind"], "sample": desc},
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
