@@ -627,9 +627,9 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   if (!c || !c->has_structure) return fail("mfe_make_local_matrix: no matrix");
   CK(cudaSetDevice(c->device));
   PhaseTimer tm(c->stream);
+  if (c->has_local) { if (num_cols) *num_cols = c->num_cols; return 0; }      // already local: keep the index maps as they are
   c->external_index.clear(); c->external_local_index.clear(); c->elements_to_send.clear();
-  c->neighbors.clear(); c->recv_length.clear(); c->send_length.clear();
-  if (c->has_local) { if (num_cols) *num_cols = c->num_cols; return 0; }
+  c->neighbors.clear(); c->recv_length.clear(); c->send_length.clear(); c->send_dst_offset.clear();
   if (c->nranks == 1) {              // make_local_matrix.hpp:51-55
     c->num_cols = c->nrows; c->has_local = true;
     c->t_make_local = tm.stop();

@@ -17,5 +17,9 @@ L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 0)
 print("nx", n, "iters", it, "dots", int(st[0]), "dirty sum/max", int(st[1]), int(st[2]), "full replays", int(st[3]), "slow gaps", int(st[4]),
       "walk ms total/max", st[5] / 1e6, st[6] / 1e6, "slowest dot #", int(st[7]), "cg DOT_s", t[1], "TOTAL_s", t[4])
 for i in range(min(int(st[0]), 40)):
-    w = int(st[16 + 2 * i]); print("  dot %3d: dirty %4d slow gaps %3d walk %.3f ms" % (i, w & 0xffffffff, w >> 32, st[17 + 2 * i] / 1e6))
+    w = int(st[16 + 2 * i])
+    try:
+        print("  dot %3d: dirty %4d slow gaps %3d walk %.3f ms" % (i, w & 0xffffffff, w >> 32, st[17 + 2 * i] / 1e6))
+    except BrokenPipeError:
+        break
 mesh.close()
