@@ -68,7 +68,8 @@ def main():
         np.savez_compressed(os.path.join(HERE, "serial_%dx%dx%d.npz" % n), **serial_case(n, full))
     for n in (32, 64):
         np.savez_compressed(os.path.join(HERE, "history_%d.npz" % n), **history_case(n))
-    for n, npr in (((2, 2, 2), 2), ((2, 2, 2), 8), ((8, 8, 8), 8), ((6, 6, 6), 4), ((5, 3, 7), 3)):
+    # the last three are the reference CI's own `mpirun -np 2` cases (.github/workflows/compare-ref-kokkos.yml:13-25,52)
+    for n, npr in (((2, 2, 2), 2), ((2, 2, 2), 8), ((8, 8, 8), 8), ((6, 6, 6), 4), ((5, 3, 7), 3), ((1, 1, 2), 2), ((17, 3, 5), 2), ((20, 30, 40), 2)):
         np.savez_compressed(os.path.join(HERE, "mpi_%dx%dx%d_np%d.npz" % (n + (npr,))), **mpi_case(n, npr))
     # boxes changed by the reference's own add_imbalance (load_imbalance percent), ref/src/driver.hpp:137-139
     for n, npr, imb in (((12, 12, 12), 8, 30), ((10, 9, 8), 4, 60), ((9, 14, 11), 6, 40)):

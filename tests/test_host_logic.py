@@ -71,7 +71,8 @@ def test_element_tables_and_matrices(H, oracle_built):
 
 
 CASES = [((4, 4, 4), 1, 100), ((5, 3, 7), 1, 2), ((2, 2, 2), 8, 1), ((8, 8, 8), 8, 3), ((6, 6, 6), 4, 100), ((5, 3, 7), 3, 1),
-         ((12, 10, 9), 5, 4), ((16, 16, 16), 2, 5), ((3, 9, 4), 7, 2), ((20, 6, 11), 6, 3), ((1, 1, 2), 1, 1), ((1, 1, 2), 2, 1)]
+         ((12, 10, 9), 5, 4), ((16, 16, 16), 2, 5), ((3, 9, 4), 7, 2), ((20, 6, 11), 6, 3), ((1, 1, 2), 1, 1), ((1, 1, 2), 2, 1),
+         ((17, 3, 5), 2, 2), ((20, 30, 40), 2, 7)]      # the reference CI's own np = 2 cases
 
 
 IMBALANCED = sorted(__import__("glob").glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpi_*_imb*.npz")))
