@@ -17,48 +17,32 @@
 
 namespace miniFE {
 
-// ref/src/SparseMatrix_functions.hpp:98-140 (row col value triplets, one file per rank); the CSR arrays are
-// exported from the device on demand
+// ref/src/SparseMatrix_functions.hpp:98-140: "<nrows> <nnz>" (rank 0 only), then "<row> <col> <value>" per stored entry,
+// rows in order.  The matrix lives on the device: its CSR arrays are exported here, on demand.
 template<typename MatrixType>
 void write_matrix(const std::string& filename,
                   MatrixType& mat)
 {
-  typedef typename MatrixType::LocalOrdinalType LocalOrdinalType;
   typedef typename MatrixType::GlobalOrdinalType GlobalOrdinalType;
   typedef typename MatrixType::ScalarType ScalarType;
-  int numprocs = 1, myproc = 0;
-#ifdef HAVE_MPI
-  MPI_Comm_size(MPI_COMM_WORLD, &numprocs);
-  MPI_Comm_rank(MPI_COMM_WORLD, &myproc);
-#endif
   b200::Entry &e = b200::entry_of(&mat, "write_matrix");
   const int64_t nrows = mfe_nrows(e.ctx), nnz = mfe_nnz(e.ctx);
-  std::vector<int64_t> ro(nrows + 1);
+  std::vector<int64_t> begin(nrows + 1);
   std::vector<int> cols(nnz);
   std::vector<double> coefs(nnz);
-  if (mfe_export_csr(e.ctx, 0, 0, &ro[0], nnz ? &cols[0] : 0, nnz ? &coefs[0] : 0) != 0) b200::die("mfe_export_csr");
-  std::ostringstream osstr;
-  osstr << filename << "." << numprocs << "." << myproc;
-  std::string full_name = osstr.str();
-  std::ofstream ofs(full_name.c_str());
-  size_t nrows_sz = mat.rows.size();
-  size_t nnz_sz = mat.num_nonzeros();      // CSRMatrix: row_offsets[nrows]; ELLMatrix: rows * num_cols_per_row (padding counted)
-  for(int p=0; p<numprocs; ++p) {
-    if (p == myproc) {
-      if (p == 0) {
-        ofs << nrows_sz << " " << nnz_sz << std::endl;
-      }
-      for(size_t i=0; i<nrows_sz; ++i) {
-        GlobalOrdinalType row = mat.rows[i];
-        for(int64_t j=ro[i]; j<ro[i+1]; ++j) {
-          ofs << row << " " << (GlobalOrdinalType)cols[j] << " " << (ScalarType)coefs[j] << std::endl;
-        }
-      }
+  if (mfe_export_csr(e.ctx, 0, 0, &begin[0], nnz ? &cols[0] : 0, nnz ? &coefs[0] : 0) != 0) b200::die("mfe_export_csr");
+  struct Lines {
+    MatrixType *A; const std::vector<int64_t> *begin; const std::vector<int> *cols; const std::vector<double> *coefs;
+    void operator()(std::ostream &os, bool is_rank0) const
+    {
+      // CSRMatrix: num_nonzeros() = row_offsets[nrows]; ELLMatrix: rows * num_cols_per_row (padding counted)
+      if (is_rank0) os << A->rows.size() << " " << (size_t)A->num_nonzeros() << std::endl;
+      for (size_t r = 0; r < A->rows.size(); ++r)
+        for (int64_t k = (*begin)[r]; k < (*begin)[r + 1]; ++k)
+          os << A->rows[r] << " " << (GlobalOrdinalType)(*cols)[k] << " " << (ScalarType)(*coefs)[k] << std::endl;
     }
-#ifdef HAVE_MPI
-    MPI_Barrier(MPI_COMM_WORLD);
-#endif
-  }
+  } lines = { &mat, &begin, &cols, &coefs };
+  b200::RankFile(filename).in_rank_order(lines);
 }
 
 // ref/src/SparseMatrix_functions.hpp:295-317 (reporting helper used by compute_matrix_stats): size of the index maps

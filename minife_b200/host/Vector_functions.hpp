@@ -22,39 +22,27 @@ inline mfe_ctx *any_context()
 }
 }
 
-// ref/src/Vector_functions.hpp:49-82 (same text format: "<row> <value>" per line, one file per rank)
+// ref/src/Vector_functions.hpp:49-82: "<local_size>" (rank 0 only), then "<global row> <value>" per entry.  The values
+// of the assembled b and of the solved x live on the device; they are fetched here.
 template<typename VectorType>
 void write_vector(const std::string& filename,
                   const VectorType& vec)
 {
-  int numprocs = 1, myproc = 0;
-#ifdef HAVE_MPI
-  MPI_Comm_size(MPI_COMM_WORLD, &numprocs);
-  MPI_Comm_rank(MPI_COMM_WORLD, &myproc);
-#endif
-  std::vector<typename VectorType::ScalarType> host(vec.coefs);
-  b200::Entry *e = b200::entry_of_vector(&vec);
-  if (e && !host.empty()) mfe_export_vector(e->ctx, e->b_vec == &vec ? "b" : "x", &host[0]);   // device copy is the truth
-  std::ostringstream osstr;
-  osstr << filename << "." << numprocs << "." << myproc;
-  std::string full_name = osstr.str();
-  std::ofstream ofs(full_name.c_str());
-  typedef typename VectorType::ScalarType ScalarType;
-  const std::vector<ScalarType>& coefs = host;
-  for(int p=0; p<numprocs; ++p) {
-    if (p == myproc) {
-      if (p == 0) {
-        ofs << vec.local_size << std::endl;
-      }
-      typename VectorType::GlobalOrdinalType first = vec.startIndex;
-      for(size_t i=0; i<vec.local_size; ++i) {
-        ofs << first+i << " " << coefs[i] << std::endl;
-      }
-    }
-#ifdef HAVE_MPI
-    MPI_Barrier(MPI_COMM_WORLD);
-#endif
+  typedef typename VectorType::ScalarType Scalar;
+  std::vector<Scalar> values(vec.coefs);
+  if (b200::Entry *e = b200::entry_of_vector(&vec)) {
+    if (!values.empty()) mfe_export_vector(e->ctx, e->b_vec == &vec ? "b" : "x", &values[0]);
   }
+  struct Lines {
+    const VectorType *v; const std::vector<Scalar> *vals;
+    void operator()(std::ostream &os, bool is_rank0) const
+    {
+      if (is_rank0) os << v->local_size << std::endl;
+      size_t row = v->startIndex;
+      for (size_t k = 0; k < (size_t)v->local_size; ++k, ++row) os << row << " " << (*vals)[k] << std::endl;
+    }
+  } lines = { &vec, &values };
+  b200::RankFile(filename).in_rank_order(lines);
 }
 
 // ref/src/Vector_functions.hpp:84-103 (host helper, kept for API completeness)
@@ -64,10 +52,11 @@ void sum_into_vector(size_t num_indices,
                      const typename VectorType::ScalarType* coefs,
                      VectorType& vec)
 {
-  typename VectorType::GlobalOrdinalType first = vec.startIndex, last = first + vec.local_size - 1;
-  for(size_t i=0; i<num_indices; ++i) {
-    if (indices[i] < first || indices[i] > last) continue;
-    vec.coefs[indices[i] - first] += coefs[i];
+  typedef typename VectorType::GlobalOrdinalType GO;
+  const GO lo = vec.startIndex, n = (GO)vec.local_size;
+  for (size_t k = 0; k < num_indices; ++k) {
+    const GO local = indices[k] - lo;
+    if (local >= 0 && local < n) vec.coefs[local] += coefs[k];     // entries of other ranks are ignored
   }
 }
 

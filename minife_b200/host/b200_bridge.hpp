@@ -11,7 +11,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <iostream>
+#include <sstream>
 #include <map>
 #include <set>
 #include <stdexcept>
@@ -66,6 +68,34 @@ inline Entry *entry_of_vector(const void *v)
     if (it->second.b_vec == v || it->second.x_vec == v) return &it->second;
   return 0;
 }
+
+// The MINIFE_DEBUG dump files (write_matrix / write_vector, ref/src/SparseMatrix_functions.hpp:98-140 and
+// ref/src/Vector_functions.hpp:49-82): one text file per rank named "<base>.<numprocs>.<rank>", written by the ranks
+// one after the other; only rank 0 writes a header line.  `body(os, is_rank0)` emits this rank's lines.
+struct RankFile {
+  int numprocs, myproc;
+  std::ofstream os;
+  explicit RankFile(const std::string &base) : numprocs(1), myproc(0)
+  {
+#ifdef HAVE_MPI
+    MPI_Comm_size(MPI_COMM_WORLD, &numprocs);
+    MPI_Comm_rank(MPI_COMM_WORLD, &myproc);
+#endif
+    std::ostringstream name;
+    name << base << '.' << numprocs << '.' << myproc;
+    os.open(name.str().c_str());
+  }
+  template<typename Body>
+  void in_rank_order(Body body)
+  {
+    for (int turn = 0; turn < numprocs; ++turn) {
+      if (turn == myproc) body(os, myproc == 0);
+#ifdef HAVE_MPI
+      MPI_Barrier(MPI_COMM_WORLD);
+#endif
+    }
+  }
+};
 
 // one context per rank: rank/size from MPI (1/0 without), boxes gathered from all ranks (they may have been
 // changed by add_imbalance, driver.hpp:137-143), GPU = rank modulo the visible device count
