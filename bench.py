@@ -28,7 +28,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 EPS = float(np.finfo(np.float64).eps)
 MAX_ITERS = 200
-PDL_DEFAULT = 0
 
 
 def weak_dims(nx, ngpus):
@@ -113,7 +112,11 @@ def measured_peaks():
 # CPU baseline: the reference's own OpenMP build (oracle/_ref/miniFE_ref_openmp.x, compiled unmodified from
 # /root/reference/openmp/src) on all host threads, on a bounded sample of the workload.
 # ------------------------------------------------------------------------------------------------------------
-def run_reference_cpu(nx, threads=None):
+def run_reference_cpu(dims, threads=None):
+    """ONE run of the reference's own OpenMP executable (openmp/src, unmodified) on `dims`; its YAML report supplies the
+    200-iteration CG timing (the sample), Mat-struc-gen Time and FE assembly Time."""
+    if isinstance(dims, int):
+        dims = [dims] * 3
     exe = os.path.join(ROOT, "oracle", "_ref", "miniFE_ref_openmp.x")
     kind = "reference"
     threads = threads or os.cpu_count() or 1
@@ -122,7 +125,7 @@ def run_reference_cpu(nx, threads=None):
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="spread")
     with tempfile.TemporaryDirectory() as d:
         t0 = time.time()
-        out = subprocess.run([exe, "nx=%d" % nx, "ny=%d" % nx, "nz=%d" % nx], cwd=d, env=env, capture_output=True, text=True, timeout=1800)
+        out = subprocess.run([exe, "nx=%d" % dims[0], "ny=%d" % dims[1], "nz=%d" % dims[2]], cwd=d, env=env, capture_output=True, text=True, timeout=3000)
         wall = time.time() - t0
         ytxt = ""
         for fn in os.listdir(d):
@@ -135,13 +138,13 @@ def run_reference_cpu(nx, threads=None):
         return float(m.group(1)) if m and m.group(1) != "inf" else None
     if out.returncode != 0 or grab("Total CG Mflops") is None:
         return None
-    return dict(kind=kind, cores=threads, wall_s=wall, iters=grab("Iterations"), cg_mflops=grab("Total CG Mflops"), cg_time=grab("Total CG Time"),
+    return dict(kind=kind, cores=threads, dims=list(dims), wall_s=wall, iters=grab("Iterations"), cg_mflops=grab("Total CG Mflops"), cg_time=grab("Total CG Time"),
                 matvec_mflops=grab("MATVEC Mflops"), struct_time=grab("Mat-struc-gen Time"), assembly_time=grab("FE assembly Time"),
                 final_resid=grab("Final Resid Norm"))
 
 
 def run_oracle_port_cpu(nx):
-    """Fallback when oracle/_ref is absent: the plain-C restatement (1 thread)."""
+    """Fallback when oracle/_ref is absent: the plain-C restatement (1 thread), on a smaller cube."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     o = Oracle(nx, nx, nx).setup()
@@ -149,34 +152,110 @@ def run_oracle_port_cpu(nx):
     t0 = time.time()
     h = o.cg_solve(MAX_ITERS, EPS)
     dt = time.time() - t0
-    return dict(kind="port", cores=1, wall_s=dt, iters=h["num_iters"], cg_mflops=1e-6 * flop_model([nx] * 3, nnz, h["num_iters"]) / dt, cg_time=dt)
+    return dict(kind="port", cores=1, dims=[nx] * 3, wall_s=dt, iters=h["num_iters"], cg_mflops=1e-6 * flop_model([nx] * 3, nnz, h["num_iters"]) / dt, cg_time=dt,
+                struct_time=None, assembly_time=None, matvec_mflops=None, final_resid=h["final_normr"] if "final_normr" in h else None)
+
+
+def cpu_sample_dims(args, dims):
+    """What the CPU arm runs: the SAME mesh as the GPU arm when the reference can hold it (int32 ordinals, host memory:
+    anything up to 256x256x512), else the per-GPU share nx^3 of it -- said so in `sample`."""
+    if args.cpu_nx:
+        return [args.cpu_nx] * 3
+    nodes = (dims[0] + 1) * (dims[1] + 1) * (dims[2] + 1)
+    return list(dims) if nodes <= 34_500_000 else [min(args.nx, 256)] * 3
+
+
+def cpu_baseline_obj(r, dims):
+    same = list(r["dims"]) == list(dims)
+    what = "reference OpenMP build (openmp/src unmodified) on all host threads" if r["kind"] == "reference" else "plain-C oracle port, 1 thread"
+    return {"value": r["cg_mflops"] / 1e3, "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"], "same_config": same,
+            "nx": r["dims"][0], "ny": r["dims"][1], "nz": r["dims"][2], "cg_iterations": int(r["iters"]), "cg_time_s": r["cg_time"],
+            "matvec_gflops": (r["matvec_mflops"] / 1e3) if r.get("matvec_mflops") else None,
+            "struct_gen_time_s": r.get("struct_time"), "fe_assembly_time_s": r.get("assembly_time"), "final_resid": r.get("final_resid"), "wall_s": r["wall_s"],
+            "sample": "%s, ONE run of nx=%d ny=%d nz=%d (%s): its own full 200-iteration cg_solve timing (%d iterations, %.1f s), %.1f s wall in all" % (
+                what, r["dims"][0], r["dims"][1], r["dims"][2], "the same mesh as the GPU arm" if same else "a bounded sample of the %dx%dx%d workload" % tuple(dims),
+                int(r["iters"]), r["cg_time"], r["wall_s"])}
 
 
 def reference_arm(args, rank):
-    """--impl reference: the reference's CPU implementation, timed on the host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU implementation, timed on the host cores (rank 0 only).  The executable runs ONCE
+    per invocation: its 200-iteration cg_solve is the sample, --steps/--warmup are echoed but add nothing (repeating a
+    40-second CPU solve 25 times would not make the number better)."""
     if rank != 0:
         return 0
-    sample = args.cpu_nx
-    vals, last = [], None
-    for i in range(args.warmup + args.steps):
-        r = run_reference_cpu(sample) or run_oracle_port_cpu(min(sample, 96))
-        if i >= args.warmup:
-            vals.append(r)
-        last = r
-    gf = float(np.mean([v["cg_mflops"] for v in vals])) / 1e3
-    ms = float(np.mean([v["cg_time"] for v in vals])) * 1e3
     dims = [args.nx] * 3 if args.strong else weak_dims(args.nx, args.gpus)
-    desc = "reference %s build, nx=ny=nz=%d (bounded sample of the %dx%dx%d workload), %d host threads, full 200-iteration cg_solve per step" % (
-        "OpenMP (openmp/src, unmodified)" if last["kind"] == "reference" else "C port", sample, dims[0], dims[1], dims[2], last["cores"])
+    r = run_reference_cpu(cpu_sample_dims(args, dims)) or run_oracle_port_cpu(96)
+    cb = cpu_baseline_obj(r, dims)
+    gf, ms = cb["value"], r["cg_time"] * 1e3
     line = {"impl": "reference", "metric": "cg_gflops", "value": gf, "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "miniFE %dx%dx%d hex8 Poisson (%s), assembled on device, 200-iteration unpreconditioned CG" % (
                            dims[0], dims[1], dims[2], "strong scaling: fixed global mesh" if args.strong else "%d^3 elements per GPU" % args.nx),
-                       "sample": desc, "parallelism": "reference OpenMP build on %d host threads (no GPU)" % last["cores"], "flop_model": "ref/src/driver.hpp:322-341"},
-            "cpu_baseline": {"value": gf, "unit": "GFLOP/s", "cores": last["cores"], "kind": last["kind"], "sample": desc},
+                       "sample": cb["sample"], "parallelism": "reference OpenMP build on %d host threads (no GPU)" % r["cores"], "flop_model": "ref/src/driver.hpp:322-341",
+                       "runs": 1},
+            "cpu_baseline": cb,
             "e2e": {"value": gf, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
+
+
+def golden_for(dims, world):
+    """The unmodified reference's record of this very configuration, if tests/golden holds one: per-iteration histories and
+    CRC-32s of the solution (tests/golden/make_big_golden.py: ref/src over the MPI shim at np = world; history_<n>.npz: serial)."""
+    g = os.path.join(ROOT, "tests", "golden")
+    fn = os.path.join(g, "big_%dx%dx%d_np%d.npz" % (dims[0], dims[1], dims[2], world))
+    if os.path.exists(fn):
+        return fn, np.load(fn)
+    if world == 1 and dims[0] == dims[1] == dims[2]:
+        fn = os.path.join(g, "history_%d.npz" % dims[0])
+        if os.path.exists(fn):
+            return fn, np.load(fn)
+    return None, None
+
+
+def check_parity(mesh, mf, L, dims, rank, world, dist, torch, iters, hist):
+    """Compare the solve just timed (free-running, no reference in the loop) with the golden record of the reference at the
+    same np: iteration count, the whole normr history and the CRC-32 of this rank's solution, all bit for bit.  A mismatch
+    ends the bench with an error; without a golden the solve is at least verified against the analytic solution."""
+    import zlib
+    fn, g = golden_for(dims, world)
+    if g is None:
+        rc, gmax, _ = mf.verify_solution(mesh, None, 0.06, False, info=True)
+        if rc != 0:
+            raise SystemExit("parity: verify_solution FAILED (max error %.3g > 0.06) and there is no golden for %s np=%d" % (gmax, dims, world))
+        return "no golden for %dx%dx%d np=%d (the reference does not fit this container's memory at that size); verify_solution ok, max error %.3g" % (
+            dims[0], dims[1], dims[2], world, gmax)
+    want = g["normr"]
+    bad = []
+    if iters != len(want) - 1:
+        bad.append("iterations %d vs %d" % (iters, len(want) - 1))
+    k = min(iters, len(want) - 1)
+    if not np.array_equal(hist[:k + 1].view(np.int64), want[:k + 1].view(np.int64)):
+        i = int(np.argmax(hist[:k + 1].view(np.int64) != want[:k + 1].view(np.int64)))
+        bad.append("normr history differs from iteration %d (%.17g vs %.17g)" % (i, hist[i], want[i]))
+    x = np.zeros(int(L.mfe_nrows(mesh._h)))
+    L.mfe_export_vector(mesh._h, b"x", x)
+    key = "crc_x_%d" % rank if ("crc_x_%d" % rank) in g.files else ("crc_x" if "crc_x" in g.files else None)
+    if key is not None and np.uint32(zlib.crc32(x.tobytes())) != np.uint32(g[key]):
+        bad.append("CRC-32 of the solution on rank %d differs" % rank)
+    nbad = len(bad)
+    if dist:
+        t = torch.tensor([nbad], device="cuda")
+        dist.all_reduce(t)
+        nbad = int(t)
+    if nbad:
+        raise SystemExit("PARITY FAILURE against %s: %s" % (os.path.basename(fn), "; ".join(bad) or "on another rank"))
+    return "golden np=%d ok (%s: %d residual norms and the solution CRC on every rank bit-equal to the unmodified reference)" % (world, os.path.basename(fn), k + 1)
+
+
+def traffic_for(dims, world):
+    """dram__bytes_read + dram__bytes_write of one SpMV launch from an `ncu --set full` capture of THIS configuration
+    (profiles/matvec_traffic_<nx>x<ny>x<nz>_np<N>.json), else None."""
+    fn = os.path.join(ROOT, "profiles", "matvec_traffic_%dx%dx%d_np%d.json" % (dims[0], dims[1], dims[2], world))
+    if os.path.exists(fn):
+        with open(fn) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -188,13 +267,14 @@ def main():
     ap.add_argument("--nx", type=int, default=256, help="elements per GPU per dimension (weak scaling), or of the whole mesh with --strong")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the global mesh is nx^3 whatever --gpus is (BASELINE.json configs[2]: --nx 400 --strong)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-nx", type=int, default=128, help="size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-nx", type=int, default=0, help="force the CPU baseline onto an nx^3 cube (default 0: the GPU arm's own mesh when the reference can hold it)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dot-mode", type=int, default=0)
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"], help="N > 1: halo exchange and dot all-reduce over NVLink peer stores "
                     "(default; falls back to NCCL when CUDA IPC is unavailable) or over NCCL send/recv + allgather")
-    ap.add_argument("--pdl", type=int, default=PDL_DEFAULT, help="programmatic dependent launch of the CG-loop kernels (1/0)")
     ap.add_argument("--no-overlap", action="store_true", help="peer mode: do not overlap the halo exchange with the interior SpMV tiles")
+    ap.add_argument("--overlap", type=int, default=1, help="peer mode: 1 = one fused SpMV launch (pack, interior tiles, wait, boundary tiles), 2 = the same as four launches, 0 = none")
+    ap.add_argument("--x-overlap", type=int, default=1, help="1: x += alpha*p runs on a second, low-priority stream beside the dot kernels; 0: fused into the r update")
     ap.add_argument("--op-timing", type=int, default=2, help="CUDA events inside the timed solves: 2 = around every SpMV launch (roofline), 1 = every op class, 0 = none")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -230,8 +310,8 @@ def main():
     mesh.set_dot_mode(args.dot_mode)
     mesh.set_op_timing(args.op_timing)
     mesh.set_option("comm_mode", 1 if args.comm == "peer" else 0)
-    mesh.set_option("overlap", 0 if args.no_overlap else 1)
-    mesh.set_option("pdl", args.pdl)
+    mesh.set_option("overlap", 0 if args.no_overlap else args.overlap)
+    mesh.set_option("x_overlap", args.x_overlap)
 
     A = mf.CSRMatrix()
     t_setup = time.time()
@@ -260,7 +340,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def solve(host_buffers):
+    hist_buf = np.full(MAX_ITERS + 1, np.nan)
+
+    def solve(host_buffers, want_hist=False):
         """one step; returns (iters, normr, cg_times)"""
         if host_buffers:
             xnp[:] = 0.0
@@ -271,7 +353,7 @@ def main():
         it, nr = C.c_int(0), C.c_double(0)
         times = np.zeros(5)
         rc = L.mfe_cg_solve(mesh._h, xnp.ctypes.data_as(C.c_void_p) if host_buffers else None, MAX_ITERS, EPS, C.byref(it), C.byref(nr),
-                            times.ctypes.data_as(C.c_void_p), None, None, None, None)
+                            times.ctypes.data_as(C.c_void_p), hist_buf.ctypes.data_as(C.c_void_p) if want_hist else None, None, None, None)
         if rc not in (0, 2):
             raise SystemExit("cg_solve failed: %s" % L.mfe_last_error().decode())
         barrier()
@@ -296,7 +378,8 @@ def main():
         solve(False)
     # per-op-class breakdown (reference YAML rows WAXPY / DOT / MATVEC): one extra, untimed solve with events around every op
     mesh.set_op_timing(1)
-    _, _, t1, _ = solve(False)
+    it1, _, t1, _ = solve(False, want_hist=True)
+    parity = check_parity(mesh, mf, L, dims, rank, world, dist, torch, it1, hist_buf)
     cg_times = {"WAXPY_s": float(t1[0]), "DOT_s": float(t1[1]), "MATVEC_s": float(t1[2]), "TOTAL_s": float(t1[4]),
                 "note": "one untimed solve with CUDA events around every op (costs ~3 %); the timed solves record events around the SpMV only"}
     mesh.set_op_timing(args.op_timing)
@@ -326,11 +409,16 @@ def main():
     if mv_ms <= 0.0:                                   # --op-timing 0: isolated launches on the same device-resident data
         mv_ms = mesh.time_kernel("matvec_dot", 20)
     achieved = mv_bytes_rank / (mv_ms * 1e-3) / 1e9
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "r01_matvec_traffic.json")
-    if os.path.exists(tf):
-        with open(tf) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+    traffic = traffic_for(dims, world)
+    # assembly: algorithmic output 12*nnz + 8*N bytes written once; FP64 work ~6 kflop per element
+    asm_ms = mesh.phase_ms("assembly")
+    nelem_rank = float(nnz) / 27.0                      # ~ elements per rank (interior rows hold 27 entries)
+    asm_bytes = 12.0 * nnz + 8.0 * nrows
+    assembly = {"kernel": "k_assemble (elements + row-owner gather)", "bound": "hbm", "algorithmic_bytes": asm_bytes, "ms": asm_ms,
+                "achieved": asm_bytes / (asm_ms * 1e-3) / 1e9 if asm_ms > 0 else None, "peak": peak, "unit": "GB/s",
+                "frac": (asm_bytes / (asm_ms * 1e-3) / 1e9 / peak) if asm_ms > 0 else None,
+                "fp64_gflop": 6.0e-6 * nelem_rank, "structure_ms": mesh.phase_ms("structure"),
+                "dirichlet_ms": mesh.phase_ms("dirichlet0") + mesh.phase_ms("dirichlet1"), "make_local_ms": mesh.phase_ms("make_local")}
     roofline = {"kernel": "k_matvec (CSR SpMV, TMA-staged)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": mv_bytes_rank, "ms_per_launch": mv_ms,
                 "cg_iteration": {"achieved": hbm_gbs / world, "frac": hbm_gbs / world / peak, "frac_of_8TBs": hbm_gbs / world / 8000.0}}
@@ -338,12 +426,8 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            r = run_reference_cpu(args.cpu_nx) or run_oracle_port_cpu(min(args.cpu_nx, 96))
-            cpu = {"value": r["cg_mflops"] / 1e3, "unit": "GFLOP/s", "cores": r["cores"], "kind": r["kind"],
-                   "sample": "%s, nx=ny=nz=%d, full 200-iteration cg_solve (%d iterations run), %.1f s wall; its FE assembly %.3g s, structure %.3g s" % (
-                       "reference OpenMP build (openmp/src unmodified) on all host threads" if r["kind"] == "reference" else "plain-C oracle port, 1 thread",
-                       args.cpu_nx if r["kind"] == "reference" else min(args.cpu_nx, 96), int(r["iters"]), r["wall_s"],
-                       r.get("assembly_time") or float("nan"), r.get("struct_time") or float("nan"))}
+            r = run_reference_cpu(cpu_sample_dims(args, dims)) or run_oracle_port_cpu(96)
+            cpu = cpu_baseline_obj(r, dims)
         line = {
             "metric": "cg_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -353,7 +437,7 @@ def main():
                        "comm": (None if world == 1 else ("NCCL send/recv + allgather" if args.comm == "nccl" else
                                 "NVLink peer stores (halo + dot all-reduce)%s" % ("" if args.no_overlap else ", halo overlapped with the interior SpMV tiles"))),
                        "l2": "inputs larger than L2 (%.1f GB per iteration per GPU vs 126 MB)" % ((12.0 * nnz + 116.0 * nrows) / 1e9), "dot": ["exact (order-reproducing)", "serial", "tree"][args.dot_mode],
-                       "flop_model": "ref/src/driver.hpp:322-341", "pdl": bool(args.pdl)},
+                       "flop_model": "ref/src/driver.hpp:322-341"},
             "hbm_gbs": hbm_gbs, "hbm_gbs_per_gpu": hbm_gbs / world, "pct_of_8TBs_per_gpu": 100.0 * hbm_gbs / world / 8000.0,
             "ms_per_cg_iteration": t_step * 1e3 / max(iters, 1), "cg_times": cg_times,
             "setup_ms": {"structure": mesh.phase_ms("structure"), "assembly": mesh.phase_ms("assembly"), "assembly_elem": mesh.phase_ms("assembly_elem"),
@@ -364,6 +448,8 @@ def main():
                     "ms_per_step": e2e_t * 1e3, "what": "mfe_cg_solve with host x (pinned): H2D x0 + 200-iteration solve + D2H x and histories, wall clock, max over ranks"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "assembly": assembly,
+            "parity": parity,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line))

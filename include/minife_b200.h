@@ -85,8 +85,7 @@ int mfe_set_dot_mode(mfe_ctx *ctx, int mode);
 /* knobs: "matvec_config" = index into the SpMV (warps, stages, gather batches) table; "comm_mode" = 1 NVLink peer
  * stores for halo + dot all-reduce (default when every rank can map every other rank's mailbox through CUDA IPC),
  * 0 NCCL send/recv + allgather; "overlap" = 1 run the SpMV tiles that need no halo while the halo is in flight
- * (peer mode); "peer_timeout_ms" = bound of every peer spin (default 30000); "dot_maps_warps" = 0 | 16 | 24; "pdl" = 1 launch the
- * CG-loop kernels with programmatic stream serialization; "fused" = 1 MINIFE_FUSED reporting (cg_solve.hpp:172-176,
+ * (peer mode); "peer_timeout_ms" = bound of every peer spin (default 30000); "dot_maps_warps" = 0 | 16 | 24; "fused" = 1 MINIFE_FUSED reporting (cg_solve.hpp:172-176,
  * 203-206): SpMV + dot(Ap,p) are timed as cg_times[MATVECDOT] (the values are bit-identical either way) */
 int mfe_set_option(mfe_ctx *ctx, const char *name, int64_t value);
 /* CUDA events inside mfe_cg_solve: 1 = around every op class, filling cg_times[WAXPY,DOT,MATVEC] (default);

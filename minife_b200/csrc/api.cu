@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -99,12 +100,25 @@ struct PeerComm {
   int *d_err = nullptr;
 };
 
+// CUDA events are created once per context and reused by every solve (no create/destroy inside the timed region, and
+// nothing to leak on an error return)
+struct EventPool {
+  std::vector<cudaEvent_t> ev; size_t used = 0;
+  cudaEvent_t get() { if (used == ev.size()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); ev.push_back(e); } return ev[used++]; }
+  void reset() { used = 0; }
+  void destroy() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); ev.clear(); used = 0; }
+};
+
 struct mfe_ctx {
   int rank = 0, nranks = 1, device = 0;
   MeshDesc m{};
   std::vector<RankBox> boxes;
   RankBox *d_boxes = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_x = nullptr;    // lower priority: the x update of iteration k runs here, beside the latency-bound dot kernels
+  cudaEvent_t ev_alpha = nullptr, ev_xdone = nullptr;
+  EventPool events;
+  int x_overlap = 1;                  // 1: x += alpha*p on stream_x (off the critical path), 0: fused into the r update (one stream)
   int sm_count = 148;
   int64_t launches = 0;
 
@@ -139,17 +153,19 @@ struct mfe_ctx {
   int mv_cfg = 0;                // SpMV configuration (see matvec_configs): 16 warps x 1 stage, 2 gather batches per row
   int tr = MV_TILE_ROWS;         // rows per SpMV tile
   int dot_maps_warps = 0;        // warps per CTA of k_dot_maps: 0 = default (24), else 16 or 24
+  int dot_fold = 1;              // 1: the dot walk runs in the last CTA of k_dot_maps, 0: as its own one-CTA launch
 
   // comm
   ncclComm_t_ comm = nullptr;
   PeerComm peer;
   int comm_mode = 1;             // 1: NVLink peer stores when available (default), 0: NCCL send/recv + allgather
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
-  int pdl = 0;                   // programmatic dependent launch of the CG-loop kernels (launch_cg)
   int test_no_exchange = 0;      // test hook: skip the halo exchange (the caller supplies the externals), keep the two SpMV passes
   int ell_width = 0;             // > 0: the matrix stands for the reference's ELLMatrix of that row width (padding terms in the SpMV)
   int fused = 0;                 // MINIFE_FUSED reporting: SpMV + dot(Ap,p) are timed as MATVECDOT (cg_solve.hpp:172-176)
   int64_t peer_timeout_ms = 30000;
+  bool peer_fits = true;         // EVERY rank's neighbour count fits the by-value tables of the peer kernels (agreed over NCCL)
+  bool peer_fits_local = true;
   std::vector<int> send_dst_offset;
   int *d_tiles_boundary = nullptr;          // SpMV tiles that reference external columns (second pass, after the halo)
   int64_t *d_tile_base_flagged = nullptr;   // tile_base with bit 62 set on those tiles (first pass skips them)
@@ -173,21 +189,19 @@ static int dev_alloc(T **p, int64_t n)
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
 
-// Launch of a CG-loop kernel.  With ctx->pdl the kernel is launched with programmatic stream serialization
-// (programmatic dependent launch): its CTAs may become resident while the previous kernel of the stream drains and
-// run up to their griddepcontrol.wait (first statement of every such kernel), which hides the launch latency and
-// the drain/ramp gap at each of the ~7 kernel boundaries of a CG iteration.
+// Launch of a CG-loop kernel on the context stream (counts the launch for mfe_launch_count).
+template <typename... P, typename... A>
+static cudaError_t launch_on(mfe_ctx *c, cudaStream_t st, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A &&...args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  c->launches++;
+  return cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...);
+}
 template <typename... P, typename... A>
 static cudaError_t launch_cg(mfe_ctx *c, void (*kern)(P...), dim3 grid, dim3 block, size_t smem, A &&...args)
 {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
-  c->launches++;
-  return cudaLaunchKernelEx(&cfg, kern, P(std::forward<A>(args))...);
+  return launch_on(c, c->stream, kern, grid, block, smem, std::forward<A>(args)...);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -277,7 +291,12 @@ extern "C" mfe_ctx *mfe_create(int rank, int nranks, int device, const int globa
   c->rank = rank; c->nranks = nranks; c->device = device; c->sm_count = prop.multiProcessorCount;
   fill_mesh(c, global_box, all_boxes);
   if (c->m.nrows < 1) { fail("mfe_create: rank %d owns no rows (ref/src/main.cpp:116-130 rejects such runs)", rank); delete c; return nullptr; }
-  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return nullptr; }
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess ||
+      (e = cudaStreamCreateWithPriority(&c->stream_x, cudaStreamNonBlocking, prio_lo)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->ev_alpha, cudaEventDisableTiming)) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&c->ev_xdone, cudaEventDisableTiming)) != cudaSuccess) { fail("cudaStreamCreate: %s", cudaGetErrorString(e)); delete c; return nullptr; }
   if (dev_alloc(&c->d_boxes, nranks)) { delete c; return nullptr; }
   cudaMemcpy(c->d_boxes, c->boxes.data(), sizeof(RankBox) * nranks, cudaMemcpyHostToDevice);
   c->m.boxes = c->d_boxes;
@@ -303,7 +322,7 @@ static void free_vectors(mfe_ctx *c)
   free_dev(c->dot.chunk_sums_a); free_dev(c->dot.piece_sums_a); free_dev(c->dot.chunk_sums_b); free_dev(c->dot.piece_sums_b);
   free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps); free_dev(c->dot.w.chunk_cnt);
   free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.warp_maps); free_dev(c->dot.w.super_maps); free_dev(c->dot.w.hyper_maps);
-  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.w.stats);
+  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.done_cnt); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.w.stats);
   c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = nullptr;
   c->dot = DotWs();
   c->vec_cap = 0;
@@ -313,6 +332,7 @@ extern "C" void mfe_destroy(mfe_ctx *c)
 {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->stream_x) cudaStreamSynchronize(c->stream_x);
   if (c->stream) cudaStreamSynchronize(c->stream);
   peer_teardown(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
@@ -320,6 +340,10 @@ extern "C" void mfe_destroy(mfe_ctx *c)
   free_matrix(c); free_vectors(c);
   free_dev(c->d_boxes); free_dev(c->d_sc); free_dev(c->d_hist); free_dev(c->d_gather);
   free_dev(c->d_elements_to_send); free_dev(c->d_send_buf);
+  c->events.destroy();
+  if (c->ev_alpha) cudaEventDestroy(c->ev_alpha);
+  if (c->ev_xdone) cudaEventDestroy(c->ev_xdone);
+  if (c->stream_x) cudaStreamDestroy(c->stream_x);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -422,6 +446,25 @@ static int peer_setup(mfe_ctx *c)
   return 0;
 }
 
+// peer transport or NCCL is a decision all ranks must take alike: gather every rank's "my neighbour tables fit" flag.
+// Collective (called by every rank from mfe_make_local_matrix, and from mfe_comm_init when the maps already exist).
+static int peer_agree(mfe_ctx *c)
+{
+  c->peer_fits = c->peer_fits_local;
+  if (c->nranks == 1 || !c->comm) return 0;
+  std::vector<double> all(c->nranks);
+  const double mine = c->peer_fits_local ? 1.0 : 0.0;
+  double *d_one = nullptr;
+  if (dev_alloc(&d_one, 1)) return 1;
+  CK(cudaMemcpyAsync(d_one, &mine, 8, cudaMemcpyHostToDevice, c->stream));
+  CKN(g_nccl.AllGather(d_one, c->d_gather, 1, NCCL_FLOAT64, c->comm, c->stream));
+  CK(cudaMemcpyAsync(all.data(), c->d_gather, 8 * c->nranks, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_one);
+  for (double v : all) if (v == 0.0) c->peer_fits = false;
+  return 0;
+}
+
 extern "C" int mfe_comm_init(mfe_ctx *c, const char id128[128])
 {
   if (!c) return fail("null context");
@@ -431,7 +474,8 @@ extern "C" int mfe_comm_init(mfe_ctx *c, const char id128[128])
   ncclUniqueId_t id;
   memcpy(id.internal, id128, 128);
   CKN(g_nccl.CommInitRank(&c->comm, c->nranks, id, c->rank));
-  return peer_setup(c);
+  if (peer_setup(c)) return 1;
+  return c->has_local ? peer_agree(c) : 0;
 }
 
 // vectors + dot workspace sized for (nrows, ncols)
@@ -462,10 +506,11 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
       dev_alloc(&c->dot.w.cta_maps, nchunks + 1) || dev_alloc(&c->dot.w.leaf_maps, (nchunks + 1) * DOT_CTA_THREADS) ||
       dev_alloc(&c->dot.w.warp_maps, npieces + 8) || dev_alloc(&c->dot.w.super_maps, nchunks / 32 + 2) ||
       dev_alloc(&c->dot.w.hyper_maps, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.chunk_cnt, nchunks + 1) || dev_alloc(&c->dot.w.super_cnt, nchunks / 32 + 2) ||
-      dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) ||
+      dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.done_cnt, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) ||
       dev_alloc(&c->dot.w.result, 1) || dev_alloc(&c->dot.w.stats, DOT_STATS_WORDS)) return 1;
   CK(cudaMemsetAsync(c->dot.w.stats, 0, 8 * DOT_STATS_WORDS, c->stream));
   CK(cudaMemsetAsync(c->dot.w.dirty_count, 0, sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->dot.w.done_cnt, 0, sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->dot.w.chunk_cnt, 0, sizeof(int) * (nchunks + 1), c->stream));
   CK(cudaMemsetAsync(c->dot.w.super_cnt, 0, sizeof(int) * (nchunks / 32 + 2), c->stream));
   CK(cudaMemsetAsync(c->dot.w.hyper_cnt, 0, sizeof(int) * (nchunks / 1024 + 2), c->stream));
@@ -645,7 +690,10 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   c->recv_length = L.recv_length; c->send_length = L.send_length;
   c->send_dst_offset = L.send_dst_offset;
   c->num_cols = L.num_cols;
-  if (c->neighbors.size() > PEER_MAX_NEIGHBORS) return fail("mfe_make_local_matrix: %d neighbours (> %d)", (int)c->neighbors.size(), (int)PEER_MAX_NEIGHBORS);
+  // the peer kernels take the neighbour tables by value (PEER_MAX_NEIGHBORS entries): more neighbours than that
+  // (unaligned boxes at np >= 28, add_imbalance) go over NCCL, which has no such limit
+  c->peer_fits_local = c->neighbors.size() <= PEER_MAX_NEIGHBORS;
+  if (peer_agree(c)) return 1;
   const int n_ext = (int)c->external_index.size();
   // device: rewrite the columns (owned: col - start_row; external: external_local_index)
   std::vector<std::pair<int, int>> srt(n_ext);
@@ -682,47 +730,70 @@ struct MvCfg { int g, s, h; };
 static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {20, 1, 2}, {21, 1, 3} };
 enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
 
+// cudaFuncSetAttribute once per (kernel instantiation, device); one process may drive several GPUs from several threads
+static std::mutex g_attr_mutex;
+template <typename K>
+static int set_smem_attr_once(K kern, bool (&done)[64], int device, size_t smem)
+{
+  std::lock_guard<std::mutex> lk(g_attr_mutex);
+  if (done[device & 63]) return 0;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  done[device & 63] = true;
+  return 0;
+}
+
 template <int G, int S, int H, int MODE>
-static int launch_matvec_mode(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
+static int launch_matvec_mode(mfe_ctx *c, const MvArgs &a)
 {
   static bool attr_set[64] = { false };
   const size_t smem = (size_t)G * S * MatvecCfg::SLOT_BYTES + (size_t)G * S * 8 + 8 * 8 + 8 * 4 + 8 * 4 + 64;
   auto kern = k_matvec<G, S, H, MODE>;
-  if (!attr_set[c->device & 63]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[c->device & 63] = true;
-  }
-  if (!tile_list) nwork = c->ntiles;
+  if (set_smem_attr_once(kern, attr_set, c->device, smem)) return 1;
+  const int64_t nwork = MODE == MV_LIST ? a.nlist : c->ntiles;
   if (nwork <= 0) return 0;
   const int grid = (int)std::min<int64_t>(c->sm_count, std::max<int64_t>(1, (nwork + G - 1) / G));
-  CK(launch_cg(c, kern, dim3(grid), dim3(32 * G), smem, c->d_coefs, c->d_cols, c->d_roff, tile_base ? tile_base : c->d_tile_base, x, y, c->nrows, c->ntiles,
-               c->nnz_padded, 0, with_sums ? c->dot.piece_sums_b : nullptr, with_sums ? c->dot.chunk_sums_b : nullptr, gate, k, tile_list, nwork, c->ell_width));
+  CK(launch_cg(c, kern, dim3(grid), dim3(32 * G), smem, a));
   return 0;
 }
 
 template <int G, int S, int H>
-static int launch_matvec_cfg(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, const int *tile_list, int64_t nwork, const int64_t *tile_base)
+static int launch_matvec_cfg(mfe_ctx *c, const MvArgs &a, int mode)
 {
-  if (tile_list) return launch_matvec_mode<G, S, H, MV_LIST>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-  if (tile_base) return launch_matvec_mode<G, S, H, MV_SKIP>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-  return launch_matvec_mode<G, S, H, MV_ALL>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+  switch (mode) {
+    case MV_ALL: return launch_matvec_mode<G, S, H, MV_ALL>(c, a);
+    case MV_SKIP: return launch_matvec_mode<G, S, H, MV_SKIP>(c, a);
+    case MV_LIST: return launch_matvec_mode<G, S, H, MV_LIST>(c, a);
+    case MV_FUSED: return launch_matvec_mode<G, S, H, MV_FUSED>(c, a);
+  }
+  return fail("bad matvec mode %d", mode);
 }
 
-static int launch_matvec_local(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k,
-                               const int *tile_list = nullptr, int64_t nwork = 0, const int64_t *tile_base = nullptr)
+// one SpMV launch over this rank's matrix in the given mode (no halo exchange here except inside MV_FUSED)
+static int launch_matvec_local(mfe_ctx *c, const MvArgs &a, int mode)
 {
   switch (c->mv_cfg) {
-    case 0: return launch_matvec_cfg<16, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 1: return launch_matvec_cfg<16, 1, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 2: return launch_matvec_cfg<10, 2, 1>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 3: return launch_matvec_cfg<20, 1, 2>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
-    case 4: return launch_matvec_cfg<21, 1, 3>(c, x, y, with_sums, gate, k, tile_list, nwork, tile_base);
+    case 0: return launch_matvec_cfg<16, 1, 2>(c, a, mode);
+    case 1: return launch_matvec_cfg<16, 1, 1>(c, a, mode);
+    case 2: return launch_matvec_cfg<10, 2, 1>(c, a, mode);
+    case 3: return launch_matvec_cfg<20, 1, 2>(c, a, mode);
+    case 4: return launch_matvec_cfg<21, 1, 3>(c, a, mode);
   }
   return fail("bad matvec configuration %d", c->mv_cfg);
 }
 
+static MvArgs mv_args(mfe_ctx *c, const double *x, double *y, bool with_sums, const CgScalars *gate, int k, bool seed_y)
+{
+  MvArgs a{};
+  a.coefs = c->d_coefs; a.cols = c->d_cols; a.roff = c->d_roff;
+  a.tile_base = c->d_tile_base; a.tile_base_flagged = c->d_tile_base_flagged;
+  a.x = x; a.y = y; a.nrows = c->nrows; a.ntiles = c->ntiles; a.nnz_padded = c->nnz_padded; a.zmask = 0;
+  a.piece_sums = with_sums ? c->dot.piece_sums_b : nullptr; a.chunk_sums = with_sums ? c->dot.chunk_sums_b : nullptr;
+  a.gate = gate; a.k = k; a.tile_list = c->d_tiles_boundary; a.nlist = c->n_boundary; a.ell_width = c->ell_width; a.seed_y = seed_y ? 1 : 0;
+  return a;
+}
+
 // halo exchange on the context stream: ref/src/exchange_externals.hpp:44-161
-static bool use_peer(const mfe_ctx *c) { return c->nranks > 1 && c->comm_mode == 1 && c->peer.ok; }
+static bool use_peer(const mfe_ctx *c) { return c->nranks > 1 && c->comm_mode == 1 && c->peer.ok && c->peer_fits; }
 
 // NCCL path: pack + grouped send/recv per neighbour (complete when the stream reaches the next kernel)
 static int exchange_nccl(mfe_ctx *c, double *x, const CgScalars *gate, int k)
@@ -740,16 +811,10 @@ static int exchange_nccl(mfe_ctx *c, double *x, const CgScalars *gate, int k)
   return 0;
 }
 
-// first half: peer mode stores my boundary values into the neighbours' halo buffers; NCCL mode does everything
-static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+// peer mode: where my boundary values go (PeerHalo) and whose flags I wait for (PeerWait) in halo epoch `epoch`
+static void peer_halo_args(mfe_ctx *c, unsigned long long epoch, PeerHalo &ph, PeerWait &pw)
 {
-  if (c->nranks == 1 || c->test_no_exchange) return 0;
-  if (!c->comm) return fail("exchange_externals: nranks > 1 but mfe_comm_init was not called");
-  if (!use_peer(c)) return exchange_nccl(c, x, gate, k);
-  const unsigned long long epoch = ++c->peer.halo_epoch;
-  const int nsend = (int)c->elements_to_send.size();
-  if (nsend == 0) return 0;
-  PeerHalo ph{};
+  ph = PeerHalo{}; pw = PeerWait{};
   int n = 0, so = 0;
   for (size_t i = 0; i < c->neighbors.size(); ++i) {
     if (c->send_length[i] <= 0) continue;
@@ -760,6 +825,23 @@ static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
     so += c->send_length[i]; ++n;
   }
   ph.start[n] = so; ph.n = n;
+  n = 0;
+  for (size_t i = 0; i < c->neighbors.size(); ++i)
+    if (c->recv_length[i] > 0) pw.flag[n++] = peer_halo_flags(c, c->rank) + c->neighbors[i];
+  pw.n = n;
+}
+
+// first half: peer mode stores my boundary values into the neighbours' halo buffers; NCCL mode does everything
+static int exchange_begin(mfe_ctx *c, double *x, const CgScalars *gate, int k)
+{
+  if (c->nranks == 1 || c->test_no_exchange) return 0;
+  if (!c->comm) return fail("exchange_externals: nranks > 1 but mfe_comm_init was not called");
+  if (!use_peer(c)) return exchange_nccl(c, x, gate, k);
+  const unsigned long long epoch = ++c->peer.halo_epoch;
+  const int nsend = (int)c->elements_to_send.size();
+  if (nsend == 0) return 0;
+  PeerHalo ph; PeerWait pw;
+  peer_halo_args(c, epoch, ph, pw);
   CK(launch_cg(c, k_pack_peer, dim3(grid_for(nsend, 256)), dim3(256), 0, x, c->d_elements_to_send, nsend, ph, epoch, c->peer.d_ticket, gate, k));
   return 0;
 }
@@ -770,14 +852,11 @@ static int exchange_end(mfe_ctx *c, double *x, const CgScalars *gate, int k)
   const int n_ext = (int)(c->num_cols - c->nrows);
   if (n_ext <= 0) return 0;
   const unsigned long long epoch = c->peer.halo_epoch;
-  PeerWait pw{};
-  int n = 0;
-  for (size_t i = 0; i < c->neighbors.size(); ++i)
-    if (c->recv_length[i] > 0) pw.flag[n++] = peer_halo_flags(c, c->rank) + c->neighbors[i];
-  pw.n = n;
+  PeerHalo ph; PeerWait pw;
+  peer_halo_args(c, epoch, ph, pw);
   const int grid = std::max(1, std::min(32, (n_ext + 2047) / 2048));
   CK(launch_cg(c, k_halo_wait_copy, dim3(grid), dim3(256), 0, pw, epoch, peer_halo_buf(c, c->rank, epoch), x + c->nrows, n_ext,
-               (unsigned long long)c->peer_timeout_ms * 1000000ULL, c->peer.d_err, gate, k));
+               (unsigned long long)c->peer_timeout_ms * 1000000ULL, c->peer.d_err, gate ? c->d_sc : nullptr, gate, k));
   return 0;
 }
 static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
@@ -786,35 +865,53 @@ static int exchange(mfe_ctx *c, double *x, const CgScalars *gate, int k)
   return exchange_end(c, x, gate, k);
 }
 
-static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k)
+// y = A x including the halo exchange (matvec_std::operator(), SparseMatrix_functions.hpp:546-578).
+// overlap 1 (default): one fused launch (MV_FUSED); overlap 2: pack / interior pass / wait + copy / boundary pass as four
+// launches (the round-1 scheme, kept for comparison); overlap 0 or NCCL: exchange, then one pass over all tiles.
+// fill_tail: the caller reads the external tail of x afterwards (API calls; the CG loop never does).
+static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const CgScalars *gate, int k, bool seed_y, bool fill_tail)
 {
+  MvArgs a = mv_args(c, x, y, with_sums, gate, k, seed_y);
+  const bool two_sets = c->n_interior > 0 && c->n_boundary > 0;
+  if ((use_peer(c) || (c->test_no_exchange && c->nranks > 1)) && c->overlap == 1 && two_sets) {
+    a.halo = x + c->nrows;                                  // test hook: the caller supplied the externals in the tail of x
+    if (use_peer(c) && !c->test_no_exchange) {
+      if (!c->comm) return fail("matvec: nranks > 1 but mfe_comm_init was not called");
+      const unsigned long long epoch = ++c->peer.halo_epoch;
+      peer_halo_args(c, epoch, a.ph, a.pw);
+      a.halo = peer_halo_buf(c, c->rank, epoch);
+      a.elements_to_send = c->d_elements_to_send; a.nsend = (int)c->elements_to_send.size();
+      a.epoch = epoch; a.timeout_ns = (unsigned long long)c->peer_timeout_ms * 1000000ULL;
+      a.ticket = c->peer.d_ticket; a.err = c->peer.d_err; a.sc = gate ? c->d_sc : nullptr;
+    }
+    if (launch_matvec_local(c, a, MV_FUSED)) return 1;
+    return fill_tail ? exchange_end(c, x, gate, k) : 0;
+  }
   if (exchange_begin(c, x, gate, k)) return 1;
-  if ((use_peer(c) || c->test_no_exchange) && c->overlap && c->n_interior > 0 && c->n_boundary > 0) {
-    if (launch_matvec_local(c, x, y, with_sums, gate, k, nullptr, 0, c->d_tile_base_flagged)) return 1;   // skips the tiles that need the halo
+  if ((use_peer(c) || c->test_no_exchange) && c->overlap == 2 && two_sets) {
+    if (launch_matvec_local(c, a, MV_SKIP)) return 1;       // skips the tiles that need the halo
     if (exchange_end(c, x, gate, k)) return 1;
-    return launch_matvec_local(c, x, y, with_sums, gate, k, c->d_tiles_boundary, c->n_boundary);
+    return launch_matvec_local(c, a, MV_LIST);
   }
   if (exchange_end(c, x, gate, k)) return 1;
-  return launch_matvec_local(c, x, y, with_sums, gate, k);
+  return launch_matvec_local(c, a, MV_ALL);
 }
 
-static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, ScalarArg b, const double *y, double *w, const CgScalars *gate, int k)
+static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, ScalarArg b, const double *y, double *w, const CgScalars *gate, int k,
+                          cudaStream_t st = nullptr)
 {
   const int64_t n2 = std::max<int64_t>(1, n / 2);
   const int grid = (int)std::min<int64_t>((n2 + 255) / 256, (int64_t)c->sm_count * 16);
-  launch_cg(c, k_waxpby, dim3(grid), dim3(256), 0, n, a, x, b, y, w, gate, k);
+  launch_on(c, st ? st : c->stream, k_waxpby, dim3(grid), dim3(256), 0, n, a, x, b, y, w, gate, k);
 }
 
 template <bool SAME, int NW>
-static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
+static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k, bool fold, const WalkArgs &wa)
 {
   static bool attr_set[64] = { false };
   const size_t smem = DotMapsCfg<SAME, NW>::SMEM_BYTES;
   auto kern = k_dot_maps<SAME, NW>;
-  if (!attr_set[c->device & 63]) {
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set[c->device & 63] = true;
-  }
+  if (set_smem_attr_once(kern, attr_set, c->device, smem)) return 1;
   const int64_t npieces = (n + DOT_PIECE - 1) / DOT_PIECE;
   if (npieces == 0) return 0;
   // one persistent CTA per SM owning a contiguous range of pieces (more CTAs only when a range would overflow the table)
@@ -822,20 +919,20 @@ static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const dou
   grid = std::max<int64_t>(grid, (npieces + DOT_MAPS_MAX_PP - 1) / DOT_MAPS_MAX_PP);
   const int PP = (int)((npieces + grid - 1) / grid);
   grid = (npieces + PP - 1) / PP;
-  CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
+  CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k, fold ? 1 : 0, wa));
   return 0;
 }
 
-static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
+static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k, bool fold, const WalkArgs &wa)
 {
   if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail("dot: operands must be 16-byte aligned");
   const int nw = c->dot_maps_warps ? c->dot_maps_warps : 24;
-  if (x == y) return nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k);
-  return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k);
+  if (x == y) return nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k, fold, wa) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k, fold, wa);
+  return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k, fold, wa) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k, fold, wa);
 }
 
 // local dot of x,y (n terms) + rank-ordered global sum + CG scalar epilogue.
-// sums_kind: where the prediction sums come from: 0 = nowhere yet (k_chunk_sums here), 1 = k_xr_update (pair a),
+// sums_kind: where the prediction sums come from: 0 = nowhere yet (k_chunk_sums here), 1 = the r update (pair a),
 //            2 = the SpMV (pair b)
 static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, int sums_kind, int epi, int k, bool gated, double *hist)
 {
@@ -865,8 +962,11 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
       CK(launch_cg(c, k_chunk_prefix, dim3(1), dim3(1024), 0, w.chunk_sums, nchunks, w.chunk_prefix, gate, k));
       CK(launch_cg(c, k_dot_tree_finish, dim3(1), dim3(1), 0, w.chunk_prefix, nchunks, w.result, sc, epi_local, k, nh, rh, ph, ah, gate));
     } else {
-      if (launch_dot_maps(c, n, x, y, w, gate, k)) return 1;
-      CK(launch_cg(c, k_dot_walk, dim3(1), dim3(WALK_THREADS), 0, n, x, y, w, sc, peer ? epi : epi_local, k, nh, rh, ph, ah, gate, pd));
+      WalkArgs wa{};
+      wa.sc = sc; wa.epi = peer ? epi : epi_local; wa.k = k; wa.normr_hist = nh; wa.rtrans_hist = rh; wa.pap_hist = ph; wa.alpha_hist = ah; wa.pd = pd;
+      const bool fold = c->dot_fold != 0 && n > 0;      // the walk runs in the last CTA of the maps kernel
+      if (launch_dot_maps(c, n, x, y, w, gate, k, fold, wa)) return 1;
+      if (!fold) CK(launch_cg(c, k_dot_walk, dim3(1), dim3(WALK_THREADS), 0, n, x, y, w, gate, wa));
       finished = peer;
     }
   }
@@ -882,16 +982,16 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
 // ---------------------------------------------------------------------------------------------------------
 // cg_solve: ref/src/cg_solve.hpp:69-229
 // ---------------------------------------------------------------------------------------------------------
-struct OpTimer {          // CUDA-event pairs per op class, resolved after the solve (no host sync inside)
+struct OpTimer {          // CUDA-event pairs per op class from the context's pool, resolved after the solve (no host sync inside)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[4];     // WAXPY, DOT, MATVEC, MATVECDOT
-  cudaStream_t s; int mode;      // 0: none, 1: every op class, 2: MATVEC only (two events per iteration)
-  OpTimer(cudaStream_t st, int m) : s(st), mode(m) {}
+  mfe_ctx *c; int mode;          // 0: none, 1: every op class, 2: MATVEC only (two events per iteration)
+  OpTimer(mfe_ctx *ctx, int m) : c(ctx), mode(m) {}
   bool on(int cls) const { return mode == 1 || (mode == 2 && (cls == MFE_MATVEC || cls == MFE_MATVECDOT)); }
-  void begin(int cls) { if (!on(cls)) return; cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); ev[cls].push_back({ a, b }); }
-  void end(int cls) { if (!on(cls)) return; cudaEventRecord(ev[cls].back().second, s); }
+  void begin(int cls, cudaStream_t st = nullptr) { if (!on(cls)) return; cudaEvent_t a = c->events.get(), b = c->events.get(); cudaEventRecord(a, st ? st : c->stream); ev[cls].push_back({ a, b }); }
+  void end(int cls, cudaStream_t st = nullptr) { if (!on(cls)) return; cudaEventRecord(ev[cls].back().second, st ? st : c->stream); }
   double total_s(int cls) {
     double t = 0;
-    for (auto &p : ev[cls]) { float ms = 0; cudaEventElapsedTime(&ms, p.first, p.second); t += ms; cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    for (auto &p : ev[cls]) { float ms = 0; if (cudaEventElapsedTime(&ms, p.first, p.second) == cudaSuccess) t += ms; }
     ev[cls].clear();
     return t * 1e-3;
   }
@@ -934,7 +1034,8 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
     c->hist_cap = max_iter + 1;
     if (dev_alloc(&c->d_hist, 4 * (int64_t)c->hist_cap)) return 1;
   }
-  cudaEvent_t t0, t1; cudaEventCreate(&t0); cudaEventCreate(&t1);
+  c->events.reset();
+  cudaEvent_t t0 = c->events.get(), t1 = c->events.get();
   cudaEventRecord(t0, c->stream);
   if (x_host) CK(cudaMemcpyAsync(c->d_x, x_host, n * 8, cudaMemcpyHostToDevice, c->stream));
   k_fill<<<64, 256, 0, c->stream>>>(c->d_hist, 4 * (int64_t)c->hist_cap, std::numeric_limits<double>::quiet_NaN());
@@ -948,19 +1049,45 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   CK(cudaMemsetAsync(c->d_r, 0, n * 8, c->stream));
   CK(cudaMemsetAsync(c->d_p, 0, c->num_cols * 8, c->stream));
   CK(cudaMemsetAsync(c->d_Ap, 0, n * 8, c->stream));
-  {   // the SpMV accumulates its p.Ap prediction sums into pair b; k_xr_update re-zeroes them every iteration
+  {   // the SpMV accumulates its p.Ap prediction sums into pair b; the r update re-zeroes them every iteration
     const int64_t nch = (n + DOT_CHUNK - 1) / DOT_CHUNK;
     CK(cudaMemsetAsync(c->dot.chunk_sums_b, 0, 8 * (nch + 1), c->stream));
     CK(cudaMemsetAsync(c->dot.piece_sums_b, 0, 8 * (nch * DOT_PIECES_PER_CHUNK + 1), c->stream));
   }
 
-  OpTimer ot(c->stream, c->op_timing);
+  OpTimer ot(c, c->op_timing);
   const ScalarArg one{ nullptr, 1.0 }, zero{ nullptr, 0.0 }, neg_one{ nullptr, -1.0 };
   CgScalars *sc = c->d_sc;
   double *hist = c->d_hist;
+  // x += alpha*p is the only update of the iteration that nothing waits for (cg_solve.hpp:211 vs 212): with x_overlap it
+  // runs on the low-priority stream beside the latency-bound dot kernels; p must not change before it has been read
+  const bool xov = c->x_overlap != 0;
+  bool x_pending = false;
+  auto join_x = [&]() { if (x_pending) { cudaStreamWaitEvent(c->stream, c->ev_xdone, 0); x_pending = false; } };
+  // x and r updates of iteration k (fused_waxpby, cg_solve.hpp:211-212): the r update also leaves the r.r prediction sums
+  auto launch_updates = [&](int k) -> int {
+    ot.begin(MFE_WAXPY);
+    if (xov) {
+      CK(launch_cg(c, k_xr_update<false>, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.piece_sums_a,
+                   c->dot.chunk_sums_a, c->dot.piece_sums_b, c->dot.chunk_sums_b, sc, k));
+      ot.end(MFE_WAXPY);
+      cudaEventRecord(c->ev_alpha, c->stream);             // alpha of iteration k is final on the main stream from here on
+      cudaStreamWaitEvent(c->stream_x, c->ev_alpha, 0);
+      ot.begin(MFE_WAXPY, c->stream_x);
+      launch_waxpby(c, n, one, c->d_x, ScalarArg{ &sc->alpha, 0.0 }, c->d_p, c->d_x, sc, k, c->stream_x);
+      ot.end(MFE_WAXPY, c->stream_x);
+      cudaEventRecord(c->ev_xdone, c->stream_x);
+      x_pending = true;
+    } else {
+      CK(launch_cg(c, k_xr_update<true>, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.piece_sums_a,
+                   c->dot.chunk_sums_a, c->dot.piece_sums_b, c->dot.chunk_sums_b, sc, k));
+      ot.end(MFE_WAXPY);
+    }
+    return 0;
+  };
 
   ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_x, zero, c->d_x, c->d_p, nullptr, 0); ot.end(MFE_WAXPY);           // p = x        (:124)
-  ot.begin(MFE_MATVEC); if (launch_matvec(c, c->d_p, c->d_Ap, false, nullptr, 0)) return 1; ot.end(MFE_MATVEC);         // Ap = A p     (:129)
+  ot.begin(MFE_MATVEC); if (launch_matvec(c, c->d_p, c->d_Ap, false, nullptr, 0, false, false)) return 1; ot.end(MFE_MATVEC);         // Ap = A p     (:129)
   ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_b, neg_one, c->d_Ap, c->d_r, nullptr, 0); ot.end(MFE_WAXPY);       // r = b - Ap   (:132)
   ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_r, c->d_r, 0, EPI_INIT_RR, 0, false, hist)) return 1; ot.end(MFE_DOT);   // rtrans       (:134)
 
@@ -975,21 +1102,20 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
           ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_r, zero, c->d_r, c->d_p, sc, k); ot.end(MFE_WAXPY);        // p = r (:154)
         } else {
           ot.begin(MFE_DOT); if (launch_dot(c, n, c->d_r, c->d_r, 1, EPI_RR, k, true, hist)) return 1; ot.end(MFE_DOT); // (:158)
+          join_x();                                                                                                      // p is about to change
           ot.begin(MFE_WAXPY); launch_waxpby(c, n, one, c->d_r, ScalarArg{ &sc->beta, 0.0 }, c->d_p, c->d_p, sc, k); ot.end(MFE_WAXPY);  // (:160)
         }
         // MINIFE_FUSED (cg_solve.hpp:172-176): matvec_and_dot = the same SpMV and the same serial-order dot (x[row]*sum
         // commutes), timed as one MATVECDOT interval; the SpMV always feeds the dot its prediction sums, fused or not
         const int mv_cls = c->fused ? MFE_MATVECDOT : MFE_MATVEC, pap_cls = c->fused ? MFE_MATVECDOT : MFE_DOT;
-        ot.begin(mv_cls); if (launch_matvec(c, c->d_p, c->d_Ap, c->dot_mode != MFE_DOT_SERIAL, sc, k)) return 1; if (!c->fused) ot.end(mv_cls);   // (:177)
+        ot.begin(mv_cls); if (launch_matvec(c, c->d_p, c->d_Ap, c->dot_mode != MFE_DOT_SERIAL, sc, k, false, false)) return 1; if (!c->fused) ot.end(mv_cls);   // (:177)
         if (!c->fused) ot.begin(pap_cls);
         if (launch_dot(c, n, c->d_Ap, c->d_p, c->dot_mode != MFE_DOT_SERIAL ? 2 : 0, EPI_PAP, k, true, hist)) return 1; ot.end(pap_cls);  // (:179)
       }
       resume_phase = 0;
-      ot.begin(MFE_WAXPY);                                                                                               // (:211-212)
-      CK(launch_cg(c, k_xr_update, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, sc, c->d_p, c->d_Ap, c->d_x, c->d_r, c->dot.piece_sums_a,
-                   c->dot.chunk_sums_a, c->dot.piece_sums_b, c->dot.chunk_sums_b, sc, k));
-      ot.end(MFE_WAXPY);
+      if (launch_updates(k)) return 1;                                                                                   // (:211-212)
     }
+    join_x();
     if (read_scalars(c, &h)) return 1;
     if (h.status == CG_PAUSED) {
       // cg_solve.hpp:186-200: p_ap_dot < brkdown_tol and >= 0  ->  breakdown(p_ap_dot, Ap, p)  (cg_solve.hpp:49-67)
@@ -1023,6 +1149,7 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
     if (h.status == CG_COMM_ERROR) break;
     if (h.status == CG_CONVERGED || h.stop_iter < k) break;
   }
+  join_x();
   if (read_scalars(c, &h)) return 1;
   cudaEventRecord(t1, c->stream);
   if (x_host) CK(cudaMemcpyAsync(x_host, c->d_x, n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1030,7 +1157,6 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   CK(cudaMemcpyAsync(hh.data(), c->d_hist, hh.size() * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   float ms = 0; cudaEventElapsedTime(&ms, t0, t1);
-  cudaEventDestroy(t0); cudaEventDestroy(t1);
   c->t_cg = ms;
   const int iters = std::min(h.stop_iter, max_iter);
   if (num_iters) *num_iters = iters;
@@ -1038,7 +1164,7 @@ extern "C" int mfe_cg_solve(mfe_ctx *c, double *x_host, int max_iter, double tol
   if (cg_times) {
     cg_times[MFE_WAXPY] = ot.total_s(MFE_WAXPY); cg_times[MFE_DOT] = ot.total_s(MFE_DOT); cg_times[MFE_MATVEC] = ot.total_s(MFE_MATVEC);
     cg_times[MFE_MATVECDOT] = ot.total_s(MFE_MATVECDOT); cg_times[MFE_TOTAL] = ms * 1e-3;
-  } else { ot.total_s(0); ot.total_s(1); ot.total_s(2); ot.total_s(3); }
+  }
   const size_t cap = c->hist_cap, cnt = (size_t)max_iter + 1;
   if (normr_hist) memcpy(normr_hist, hh.data(), cnt * 8);
   if (rtrans_hist) memcpy(rtrans_hist, hh.data() + cap, cnt * 8);
@@ -1070,11 +1196,12 @@ extern "C" int mfe_time_kernels(mfe_ctx *c, double *x_host, int max_iter, double
   double *d_vals = nullptr;
   if (dev_alloc(&d_vals, std::max(max_iter, 1))) return 1;
   const ScalarArg one{ nullptr, 1.0 }, zero{ nullptr, 0.0 };
-  cudaEvent_t ev[4]; for (auto &e : ev) cudaEventCreate(&e);
+  c->events.reset();
+  cudaEvent_t ev[4]; for (auto &e : ev) e = c->events.get();
   cudaEventRecord(ev[0], c->stream);
   for (int i = 0; i < max_iter; ++i) launch_waxpby(c, n, one, c->d_x, zero, c->d_x, c->d_p, nullptr, 0);
   cudaEventRecord(ev[1], c->stream);
-  for (int i = 0; i < max_iter; ++i) if (launch_matvec(c, c->d_p, c->d_x, false, nullptr, 0)) return 1;
+  for (int i = 0; i < max_iter; ++i) if (launch_matvec(c, c->d_p, c->d_x, false, nullptr, 0, true, false)) return 1;
   cudaEventRecord(ev[2], c->stream);
   for (int i = 0; i < max_iter; ++i) {
     if (launch_dot(c, n, c->d_x, c->d_p, 0, EPI_NONE, 0, false, nullptr)) return 1;
@@ -1090,7 +1217,6 @@ extern "C" int mfe_time_kernels(mfe_ctx *c, double *x_host, int max_iter, double
   if (xdotp) *xdotp = acc;
   float a = 0, b = 0, d = 0;
   cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&d, ev[2], ev[3]);
-  for (auto &e : ev) cudaEventDestroy(e);
   cudaFree(d_vals);
   if (kern_times) { kern_times[MFE_WAXPY] = a * 1e-3; kern_times[MFE_MATVEC] = b * 1e-3; kern_times[MFE_DOT] = d * 1e-3; kern_times[MFE_MATVECDOT] = 0; kern_times[MFE_TOTAL] = 0; }
   CK(cudaGetLastError());
@@ -1188,9 +1314,14 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
     c->comm_mode = (int)value;
     return 0;
   }
-  if (!strcmp(name, "overlap")) { c->overlap = value != 0; return 0; }
-  if (!strcmp(name, "pdl")) { c->pdl = value != 0; return 0; }
+  if (!strcmp(name, "overlap")) {            // 0 none, 1 one fused launch (default), 2 interior / boundary passes as separate launches
+    if (value < 0 || value > 2) return fail("mfe_set_option: overlap must be 0, 1 or 2");
+    c->overlap = (int)value;
+    return 0;
+  }
   if (!strcmp(name, "fused")) { c->fused = value != 0; return 0; }
+  if (!strcmp(name, "x_overlap")) { c->x_overlap = value != 0; return 0; }
+  if (!strcmp(name, "dot_fold")) { c->dot_fold = value != 0; return 0; }
   if (!strcmp(name, "test_no_exchange")) { c->test_no_exchange = value != 0; return 0; }
   if (!strcmp(name, "ell_width")) {          // ref/src/ELLMatrix.hpp: 0 = CSR semantics, 27 = the width generate_matrix_structure reserves
     if (value < 0 || value > 64) return fail("mfe_set_option: ell_width must be in [0,64]");
@@ -1211,7 +1342,8 @@ extern "C" int mfe_matvec(mfe_ctx *c, double *x_host, double *y_host)
   CK(cudaSetDevice(c->device));
   if (ensure_vectors(c, c->nrows, c->num_cols)) return 1;
   CK(cudaMemcpyAsync(c->d_tmp1, x_host, c->num_cols * 8, cudaMemcpyHostToDevice, c->stream));
-  if (launch_matvec(c, c->d_tmp1, c->d_tmp2, false, nullptr, 0)) return 1;
+  CK(cudaMemcpyAsync(c->d_tmp2, y_host, c->nrows * 8, cudaMemcpyHostToDevice, c->stream));      // beta*y[row] reads the caller's y
+  if (launch_matvec(c, c->d_tmp1, c->d_tmp2, false, nullptr, 0, true, true)) return 1;
   CK(cudaMemcpyAsync(y_host, c->d_tmp2, c->nrows * 8, cudaMemcpyDeviceToHost, c->stream));
   if (c->nranks > 1 && !c->test_no_exchange) CK(cudaMemcpyAsync(x_host + c->nrows, c->d_tmp1 + c->nrows, (c->num_cols - c->nrows) * 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -1406,8 +1538,8 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
   CK(cudaMemcpyAsync(c->d_sc, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
   cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
   auto body = [&](int rep) -> int {
-    if (!strcmp(what, "matvec")) return launch_matvec_local(c, c->d_p, c->d_Ap, false, nullptr, 0);
-    if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, c->d_p, c->d_Ap, true, nullptr, 0);
+    if (!strcmp(what, "matvec")) return launch_matvec_local(c, mv_args(c, c->d_p, c->d_Ap, false, nullptr, 0, false), MV_ALL);
+    if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, mv_args(c, c->d_p, c->d_Ap, true, nullptr, 0, false), MV_ALL);
     if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n, c->ell_width); c->launches++; return 0; }
     if (!strcmp(what, "stream_probe")) {
       constexpr int PG = 16, PS = 1;
@@ -1430,7 +1562,8 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
     if (!strcmp(what, "waxpby")) { launch_waxpby(c, n, one, c->d_r, half, c->d_p, c->d_tmp1, nullptr, 0); return 0; }
     if (!strcmp(what, "dot_rr")) return launch_dot(c, n, c->d_r, c->d_r, 0, EPI_NONE, 0, false, nullptr);
     if (!strcmp(what, "dot_pap")) return launch_dot(c, n, c->d_Ap, c->d_p, 0, EPI_NONE, 0, false, nullptr);
-    if (!strcmp(what, "xr_update")) { CK(launch_cg(c, k_xr_update, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.piece_sums_a, c->dot.chunk_sums_a, nullptr, nullptr, nullptr, 0)); return 0; }
+    if (!strcmp(what, "xr_update")) { CK(launch_cg(c, k_xr_update<true>, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.piece_sums_a, c->dot.chunk_sums_a, nullptr, nullptr, nullptr, 0)); return 0; }
+    if (!strcmp(what, "r_update")) { CK(launch_cg(c, k_xr_update<false>, dim3(grid_for(n, DOT_CHUNK)), dim3(DOT_CTA_THREADS), 0, n, c->d_sc, c->d_p, c->d_Ap, c->d_tmp1, c->d_tmp2, c->dot.piece_sums_a, c->dot.chunk_sums_a, nullptr, nullptr, nullptr, 0)); return 0; }
     (void)rep;
     return fail("mfe_time_kernel: unknown kernel '%s'", what);
   };

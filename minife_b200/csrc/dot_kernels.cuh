@@ -20,13 +20,14 @@ namespace mfe {
 // cg_solve.hpp:211-212 fused:  x = 1*x + alpha*p ;  r = 1*r + (-alpha)*Ap ;  plain sums of r*r per piece / chunk
 // (binade prediction for the next exact dot).  One CTA per chunk, one warp per piece (a warp instruction touches
 // 256 contiguous bytes per operand).  Also zeroes the p.Ap prediction sums that the next SpMV accumulates into.
+// WITH_X = false: the r half only; x += alpha*p then runs as a k_waxpby on the low-priority stream (api.cu, x_overlap).
+template <bool WITH_X>
 __global__ void __launch_bounds__(DOT_CTA_THREADS) k_xr_update(int64_t n, const CgScalars *sc, const double *__restrict__ p,
                                                                const double *__restrict__ Ap, double *__restrict__ x,
                                                                double *__restrict__ r, double *__restrict__ piece_sums,
                                                                double *__restrict__ chunk_sums, double *__restrict__ zero_piece_sums,
                                                                double *__restrict__ zero_chunk_sums, const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ double sh[DOT_PIECES_PER_CHUNK];
   const double alpha = sc->alpha, nalpha = sc->neg_alpha, one = 1.0;
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_xr_update(int64_t n, const 
   for (int it = 0; it < DOT_LEAF; ++it) {
     const int64_t i = base + it * 32 + lane;
     if (i < n) {
-      x[i] = __dadd_rn(__dmul_rn(one, x[i]), __dmul_rn(alpha, p[i]));
+      if (WITH_X) x[i] = __dadd_rn(__dmul_rn(one, x[i]), __dmul_rn(alpha, p[i]));
       const double rn = __dadd_rn(__dmul_rn(one, r[i]), __dmul_rn(nalpha, Ap[i]));
       r[i] = rn;
       acc += rn * rn;
@@ -65,7 +66,6 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_chunk_sums(int64_t n, const
                                                                 double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
                                                                 const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ double sh[DOT_PIECES_PER_CHUNK];
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(DOT_CTA_THREADS) k_chunk_sums(int64_t n, const
 __global__ void __launch_bounds__(1024) k_chunk_prefix(const double *__restrict__ sums, int nchunks, double *__restrict__ chunk_prefix,
                                                        const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ double wtot[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -199,6 +198,136 @@ __device__ __forceinline__ void dot_publish_chunk_map(const DotWork &w, const Do
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Exact dot, walk phase: one CTA.  (1) sort the dirty leaves, fetch their products; (2) one warp per gap: the
+// <= 9 runs of the gap are loaded at once (one map per lane and run) and collapsed by ordered shuffle scans into
+// ONE map per gap; (3) thread 0 walks  [gap 0][dirty leaf 0][gap 1][dirty leaf 1] ... [gap D]  -- ~2 short steps
+// per dirty leaf.  Any map that fails its check is replayed from global memory in plain floating point, so the
+// result is the serial loop's for every input.
+// Runs either as the tail of k_dot_maps in the CTA that finishes last (arrival ticket; no separate launch) or as the
+// kernel k_dot_walk.
+// ------------------------------------------------------------------------------------------------------
+enum { WALK_THREADS = 512 };
+
+struct WalkArgs {                 // by-value kernel argument: what happens with the local sum
+  CgScalars *sc; int epi, k;
+  double *normr_hist, *rtrans_hist, *pap_hist, *alpha_hist;
+  PeerDot pd;
+};
+struct WalkSmem {
+  int dirty[DOT_MAX_DIRTY];
+  int sorted[DOT_MAX_DIRTY];
+  DotMap gmaps[DOT_MAX_DIRTY + 1];
+  double replay_prod[DOT_MAX_DIRTY * DOT_LEAF];
+};
+
+// called by all NT threads of one CTA
+template <int NT>
+__device__ __noinline__ void dot_walk_body(int64_t n, const double *__restrict__ x, const double *__restrict__ y, const DotWork &w,
+                                          const WalkArgs &wa, WalkSmem &ws)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long t_begin = (w.stats && tid == 0) ? global_ns() : 0ULL;
+  int slow_gaps = 0;
+  const int D = __ldcg(w.dirty_count);
+  const long long nleaves = ((n + DOT_PIECE - 1) / DOT_PIECE) * 32;     // whole pieces: the maps that exist
+  double s = 0.0;
+  if (D > DOT_MAX_DIRTY) {                     // pathological input: the literal loop
+    if (tid == 0) s = dot_replay(x, y, 0, n, 0.0);
+  } else {
+    for (int i = tid; i < D; i += NT) ws.dirty[i] = __ldcg(w.dirty_list + i);
+    __syncthreads();
+    for (int i = tid; i < D; i += NT) {        // rank sort (leaf indices are distinct)
+      const int v = ws.dirty[i]; int rk = 0;
+      for (int j = 0; j < D; ++j) rk += ws.dirty[j] < v;
+      ws.sorted[rk] = v;
+    }
+    __syncthreads();
+    // products of the dirty leaves, fetched by all threads at once (the sequential walk then reads smem only)
+    for (int q = tid; q < D * DOT_LEAF; q += NT) {
+      const int64_t i = (int64_t)ws.sorted[q / DOT_LEAF] * DOT_LEAF + (q % DOT_LEAF);
+      ws.replay_prod[q] = i < n ? __dmul_rn(x[i], y[i]) : 0.0;
+    }
+    for (int g = warp; g <= D; g += NT / 32) {
+      const long long lo = g == 0 ? 0 : (long long)ws.sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)ws.sorted[g];
+      WalkPiece pc[DOT_GAP_PIECES];
+      dot_gap_decompose(lo, hi, pc);
+      // the maps of the gap in application order form one flat list; lane l takes a contiguous slice of it
+      int total = 0;
+#pragma unroll
+      for (int q = 0; q < DOT_GAP_PIECES; ++q) total += pc[q].count;
+      const int per = (total + 31) / 32, f0 = lane * per, f1 = min(total, f0 + per);
+      DotMap gm = dot_identity();
+      for (int base = f0; base < f1; base += 8) {
+        DotMap buf[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          int f = base + u;
+          if (f < f1) {
+            int q = 0;
+#pragma unroll
+            for (int t = 0; t < DOT_GAP_PIECES - 1; ++t) if (q == t && f >= pc[t].count) { f -= pc[t].count; q = t + 1; }
+            buf[u] = load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + f);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (base + u < f1) gm = dot_compose(gm, buf[u]);
+      }
+      gm = warp_compose(gm, lane);
+      if (lane == 31) ws.gmaps[g] = gm;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int g = 0; g <= D; ++g) {
+        const long long lo = g == 0 ? 0 : (long long)ws.sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)ws.sorted[g];
+        if (lo < hi && !dot_apply(ws.gmaps[g], s)) { s = dot_walk_gap_slow(lo, hi, w, x, y, n, s); ++slow_gaps; }
+        if (g < D) {
+          const int64_t b = (int64_t)ws.sorted[g] * DOT_LEAF;
+          const int cnt = (int)(b + DOT_LEAF <= n ? DOT_LEAF : n - b);
+          double pr[DOT_LEAF];
+#pragma unroll
+          for (int i = 0; i < DOT_LEAF; ++i) pr[i] = ws.replay_prod[g * DOT_LEAF + i];
+#pragma unroll
+          for (int i = 0; i < DOT_LEAF; ++i) if (i < cnt) s = __dadd_rn(s, pr[i]);
+        }
+      }
+    }
+  }
+  CgScalars *sc = wa.sc;
+  if (tid == 0) {
+    *w.dirty_count = 0;                         // ready for the next dot on this workspace
+    if (sc) sc->dot_local = s;
+    if (w.stats) {
+      // diagnostics: [0] dots, [1] sum of dirty leaves, [2] max, [3] whole-vector replays, [4] gaps that took the slow path,
+      // [5] total ns in the walk, [6] max ns, [7] dot index of the max; then a ring of (dirty leaves, ns) per dot
+      const unsigned long long dt = global_ns() - t_begin, idx = w.stats[0];
+      w.stats[0] = idx + 1; w.stats[1] += (unsigned long long)D; if ((unsigned long long)D > w.stats[2]) w.stats[2] = D;
+      if (D > DOT_MAX_DIRTY) w.stats[3] += 1;
+      w.stats[4] += (unsigned long long)slow_gaps; w.stats[5] += dt;
+      if (dt > w.stats[6]) { w.stats[6] = dt; w.stats[7] = idx; }
+      w.stats[DOT_STATS_HEAD + 2 * (idx % DOT_STATS_TRACE)] = ((unsigned long long)slow_gaps << 32) | (unsigned)D;
+      w.stats[DOT_STATS_HEAD + 2 * (idx % DOT_STATS_TRACE) + 1] = dt;
+    }
+  }
+  bool ok = true;
+  if (wa.pd.nranks > 1) s = peer_dot_allreduce(wa.pd, s, ok);     // rank-ordered global sum over NVLink peer memory
+  if (tid == 0) {
+    *w.result = s;
+    if (sc) {
+      if (!ok) { sc->status = CG_COMM_ERROR; sc->stop_iter = -1; }
+      else if (wa.epi != EPI_NONE) cg_epilogue(sc, wa.epi, wa.k, s, wa.normr_hist, wa.rtrans_hist, wa.pap_hist, wa.alpha_hist);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                                                          DotWork w, const CgScalars *gate, WalkArgs wa)
+{
+  if (cg_gate_closed(gate, wa.k)) return;
+  __shared__ WalkSmem ws;
+  dot_walk_body<WALK_THREADS>(n, x, y, w, wa, ws);
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Exact dot, map phase.  Persistent CTAs of NW independent warps; CTA b owns the contiguous pieces
 // [b*PP, (b+1)*PP).  Every warp arms its own shared-memory stage with 1-D bulk async copies (TMA engine) of the
 // 4 KB per operand of its next piece, waits on its mbarrier, and turns the piece into one DotMap:
@@ -217,15 +346,66 @@ template <bool SAME, int NW>
 struct DotMapsCfg {
   static constexpr int STAGE_BYTES = (SAME ? 1 : 2) * DOT_PIECE * 8;
   static constexpr int MAX_CHUNKS = DOT_MAPS_MAX_PP / DOT_PIECES_PER_CHUNK + 2;      // chunks a CTA's range can touch
-  static constexpr size_t SMEM_BYTES = (size_t)NW * STAGE_BYTES + (size_t)NW * 8 /*mbarriers*/ + (size_t)(DOT_MAPS_MAX_PP + 1) * 8 /*table*/ +
+  static constexpr size_t MAIN_BYTES = (size_t)NW * STAGE_BYTES + (size_t)NW * 8 /*mbarriers*/ + (size_t)(DOT_MAPS_MAX_PP + 1) * 8 /*table*/ +
                                        (size_t)2 * NW * 8 /*reductions*/ + (size_t)MAX_CHUNKS * 4 /*arrival counters*/ + 64;
+  // the folded walk reuses the stages (dead by then); it must fit whatever NW is
+  static constexpr size_t SMEM_BYTES = MAIN_BYTES > sizeof(WalkSmem) + 128 ? MAIN_BYTES : sizeof(WalkSmem) + 128;
 };
+
+// The slow path of one piece: a leaf-by-leaf treatment with the prediction refined inside the piece (binade changes,
+// exact ties, leaves near a binade end, ragged tail, zero / non-finite running sums).  Returns the piece map on lane 31
+// and stores the leaf maps + dirty leaves when there are any.  Called by a whole warp.
+template <bool SAME>
+__device__ __noinline__ DotMap dot_piece_slow(int64_t n, const double *__restrict__ x, const double *__restrict__ y, const DotWork &w, int piece,
+                                              const double *stage, double pre_begin, double pre_end, bool &piece_dirty_out)
+{
+  const int lane = threadIdx.x & 31;
+  const int64_t lbeg = (int64_t)piece * DOT_PIECE + lane * DOT_LEAF;
+  const int cnt = (int)(lbeg >= n ? 0 : (n - lbeg < DOT_LEAF ? n - lbeg : DOT_LEAF));
+  const double *xs = stage + lane * DOT_LEAF, *ys = SAME ? xs : xs + DOT_PIECE;
+  // products rounded once (fl(x*y)) exactly as the serial loop forms them
+  double prod[DOT_LEAF];
+#pragma unroll
+  for (int i = 0; i < DOT_LEAF; ++i) prod[i] = i < cnt ? __dmul_rn(xs[i], ys[i]) : 0.0;
+  double ls = 0.0;
+#pragma unroll
+  for (int i = 0; i < DOT_LEAF; ++i) ls += prod[i];
+  double inc = ls;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+  const double pre = pre_begin + (inc - ls);
+  const int hyp = dot_hyp_of(pre);
+  int hyp_end = __shfl_down_sync(0xffffffffu, hyp, 1);       // predicted binade at the start of the next leaf
+  if (lane == 31) hyp_end = dot_hyp_of(pre_end);
+
+  bool risky = false;
+  DotMap m = dot_identity();
+  if (cnt == DOT_LEAF) {
+    m = dot_leaf_map16(prod, hyp, pre);                      // simple form when far from the binade ends, else ordered with exact bounds
+    if (hyp >= 0 && hyp != HYP_ZERO) risky = dot_leaf_risky(m, hyp, pre);
+  } else if (cnt > 0) {
+    m = dot_leaf_map(x, y, lbeg, lbeg + cnt, hyp);           // ragged last leaf of the vector
+  }
+  const bool dirty = cnt > 0 && (m.hyp == HYP_INVALID || hyp != hyp_end || risky);
+  const bool piece_dirty = __any_sync(0xffffffffu, dirty);
+  const DotMap wm = warp_compose(m, lane);
+  if (piece_dirty) {
+    // keep the 32 leaf maps so that the walker can stitch around the dirty leaves of this piece
+    w.leaf_maps[(int64_t)piece * 32 + lane] = m;
+    if (dirty) {
+      const int slot = atomicAdd(w.dirty_count, 1);
+      if (slot < DOT_MAX_DIRTY) w.dirty_list[slot] = piece * 32 + lane;
+    }
+  }
+  piece_dirty_out = piece_dirty;
+  return wm;
+}
 
 template <bool SAME, int NW>
 __global__ void __launch_bounds__(32 * NW, 1)
-k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y, DotWork w, int npieces, int PP, const CgScalars *gate, int k)
+k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y, DotWork w, int npieces, int PP, const CgScalars *gate, int k,
+           int fold_walk, const __grid_constant__ WalkArgs wa)
 {
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // PDL: see launch_cg (api.cu)
   constexpr int STAGE = DotMapsCfg<SAME, NW>::STAGE_BYTES;
   constexpr int NT = 32 * NW;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -237,8 +417,8 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
   int *ccnt = reinterpret_cast<int *>(red + 2 * NW);            // arrivals per chunk of this CTA's range
   const int nchunks = (npieces + DOT_PIECES_PER_CHUNK - 1) / DOT_PIECES_PER_CHUNK;
   const int p0 = blockIdx.x * PP;
-  const int np = min(PP, npieces - p0);                         // pieces of this CTA
-  if (np <= 0) return;
+  const int np = min(PP, npieces - p0);                         // pieces of this CTA (the host sizes the grid so that np >= 1)
+  if (cg_gate_closed(gate, k)) return;
 
   auto issue = [&](int piece) {
     const int64_t b = (int64_t)piece * DOT_PIECE;
@@ -254,8 +434,6 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
   }
   for (int i = tid; i < DotMapsCfg<SAME, NW>::MAX_CHUNKS; i += NT) ccnt[i] = 0;
   __syncthreads();
-  asm volatile("griddepcontrol.wait;" ::: "memory");                    // the operands, sums and gate scalars are final from here on
-  if (cg_gate_closed(gate, k)) return;
   if (lane == 0 && wq < np) issue(p0 + wq);                     // first piece of every warp is in flight during the prologue
 
   // ---- prologue: predicted running sum at the start of every piece of this CTA ----
@@ -288,92 +466,55 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
   uint32_t parity = 0;
   for (int j = wq; j < np; j += NW) {
     const int piece = p0 + j;
-    const int64_t lbeg = (int64_t)piece * DOT_PIECE + lane * DOT_LEAF;
-    const int cnt = (int)(lbeg >= n ? 0 : (n - lbeg < DOT_LEAF ? n - lbeg : DOT_LEAF));
+    const double pre0 = table[j], pre1 = table[j + 1];
+    const int hyp0 = dot_hyp_of(pre0);
+    const int kk = 1075 - (hyp0 & 0x7ff);                       // the terms scale by 2^kk into units of the running sum's ulp
+    // Fast path: the predicted running sum keeps one binade over the whole piece.  Every leaf is then taken in the
+    // order-independent "simple" form (exact_dot.h, dot_leaf16_simple) under that one hypothesis, and the piece map gets
+    // CONSERVATIVE bounds: every partial offset of the piece lies in [sum of the negative offsets, sum of the positive
+    // ones].  Taken only when those bounds, applied to the predicted significand, stay MFE_DOT_FAR_MARGIN ulps inside
+    // the binade (so dot_apply will accept the map); anything else -- a binade change, an exact tie, a huge term, the
+    // ragged tail -- goes leaf by leaf through dot_piece_slow.
+    bool fast = (int64_t)(piece + 1) * DOT_PIECE <= n && hyp0 >= 0 && hyp0 != HYP_ZERO && hyp0 == dot_hyp_of(pre1) && kk <= 1023;
     mbar_wait(bar, parity);
     parity ^= 1u;
-    const double *xs = stage + lane * DOT_LEAF, *ys = SAME ? xs : xs + DOT_PIECE;
-    // products rounded once (fl(x*y)) exactly as the serial loop forms them
-    double prod[DOT_LEAF];
-    if (cnt == DOT_LEAF) {
-      // byte address of element i ^ rot of this lane's leaf: the leaf base is 128-byte aligned, so OR = ADD
-      const uint32_t lbase = smem_u32(xs), rotb = (uint32_t)(lane & (DOT_LEAF - 1)) * 8u;
+    DotMap wm;
+    bool piece_dirty = false;
+    if (fast) {
+      const double c = ((hyp0 >> 11) & 1) ? -dot_pow2(kk) : dot_pow2(kk);
+      double A[4] = { 0.0, 0.0, 0.0, 0.0 }, AB[4] = { 0.0, 0.0, 0.0, 0.0 };
+      unsigned dm[4] = { 0, 0, 0, 0 }, sg = 0;
+      // byte address of element i ^ rot of this lane's leaf (bank-conflict free; the leaf base is 128-byte aligned, so OR = ADD)
+      const uint32_t lbase = smem_u32(stage + lane * DOT_LEAF), rotb = (uint32_t)(lane & (DOT_LEAF - 1)) * 8u;
 #pragma unroll
       for (int i = 0; i < DOT_LEAF; ++i) {
-        const uint32_t a = lbase | ((uint32_t)(i * 8) ^ rotb);
-        const double xv = lds_f64(a);
-        prod[i] = SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(a));
+        const uint32_t ad = lbase | ((uint32_t)(i * 8) ^ rotb);
+        const double xv = lds_f64(ad);
+        const double pr = SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(ad));
+        MFE_DOT_SIMPLE_TERM(i & 3, __dmul_rn(pr, c))
       }
-    } else {
+      double asum = __dadd_rn(__dadd_rn(A[0], A[1]), __dadd_rn(A[2], A[3]));
+      double absum = __dadd_rn(__dadd_rn(AB[0], AB[1]), __dadd_rn(AB[2], AB[3]));
+      unsigned dmax = max(max(dm[0], dm[1]), max(dm[2], dm[3]));
+      // piece totals (exact integers: accepted only below 2^51, where every partial sum is exact whatever the order)
 #pragma unroll
-      for (int i = 0; i < DOT_LEAF; ++i) prod[i] = i < cnt ? __dmul_rn(xs[i], ys[i]) : 0.0;
-    }
-    double ls = 0.0;
-#pragma unroll
-    for (int i = 0; i < DOT_LEAF; ++i) ls += prod[i];
-    double inc = ls;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    const double pre = table[j] + (inc - ls);
-    const int hyp = dot_hyp_of(pre);
-    int hyp_end = __shfl_down_sync(0xffffffffu, hyp, 1);       // predicted binade at the start of the next leaf
-    if (lane == 31) hyp_end = dot_hyp_of(table[j + 1]);
-
-    bool simple = false, risky = false;
-    double sa = 0.0, slo = 0.0, shi = 0.0;
-    DotMap m = dot_identity();
-    if (cnt == DOT_LEAF && hyp >= 0 && hyp != HYP_ZERO) {
-      simple = dot_leaf16_simple(prod, hyp, pre, sa, slo, shi);
-      if (!simple) {                                           // exact tie / near a binade boundary: ordered, exact bounds
-#pragma unroll
-        for (int i = 0; i < DOT_LEAF; ++i) prod[i] = SAME ? __dmul_rn(xs[i], xs[i]) : __dmul_rn(xs[i], ys[i]);
-        m = dot_leaf_map16_fp(prod, hyp);
-        risky = dot_leaf_risky(m, hyp, pre);
+      for (int o = 16; o > 0; o >>= 1) {
+        asum = __dadd_rn(asum, __shfl_xor_sync(0xffffffffu, asum, o));
+        absum = __dadd_rn(absum, __shfl_xor_sync(0xffffffffu, absum, o));
+        dmax = max(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        sg |= __shfl_xor_sync(0xffffffffu, sg, o);
       }
-    } else if (cnt == DOT_LEAF) {
-      m = dot_leaf_map16(prod, hyp, pre);                      // hyp < 0, or the running sum is exactly +0.0 (order independent)
-    } else if (cnt > 0) {
-      m = dot_leaf_map(x, y, lbeg, lbeg + cnt, hyp);           // ragged last leaf of the vector
+      const double pos = (absum + asum) * 0.5, ng = (asum - absum) * 0.5;
+      const double Sp = __dmul_rn(pre0, c);
+      const bool nonneg = !(sg >> 31);
+      fast = dmax < 0x3fe00000u && absum < 2251799813685248.0 &&
+             (nonneg || (Sp + ng) - MFE_DOT_FAR_MARGIN > 4503599627370496.0) && (Sp + pos) + MFE_DOT_FAR_MARGIN < 9007199254740992.0;
+      wm.a0 = (long long)asum; wm.a1 = wm.a0; wm.lo = nonneg ? 1LL : (long long)ng; wm.hi = (long long)pos; wm.hyp = hyp0; wm.pad = 0;
     }
-    const bool dirty = cnt > 0 && ((!simple && m.hyp == HYP_INVALID) || hyp != hyp_end || risky);
-    const bool piece_dirty = __any_sync(0xffffffffu, dirty);
+    if (!fast) wm = dot_piece_slow<SAME>(n, x, y, w, piece, stage, pre0, pre1, piece_dirty);
     __syncwarp();
     if (lane == 0 && j + NW < np) issue(piece + NW);           // the stage is free: next piece in flight while we publish
 
-    // ordered collapse of the 32 leaves onto lane 31
-    const int hyp0 = __shfl_sync(0xffffffffu, hyp, 0);
-    const bool all_simple = __all_sync(0xffffffffu, simple && hyp == hyp0);
-    DotMap wm;
-    if (all_simple) {
-      // simple maps compose in floating point: a = fa + ga, lo = min(flo, fa + glo), hi = max(fhi, fa + ghi); every
-      // value is an exact integer while below 2^53, and a map that ever exceeds 2^52 is unusable (checked below)
-      double ca = sa, clo = slo, chi = shi;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double fa = __shfl_up_sync(0xffffffffu, ca, o), flo = __shfl_up_sync(0xffffffffu, clo, o), fhi = __shfl_up_sync(0xffffffffu, chi, o);
-        if (lane >= o) {
-          const double nlo = fa + clo, nhi = fa + chi;
-          clo = flo < nlo ? flo : nlo;
-          chi = fhi > nhi ? fhi : nhi;
-          ca = fa + ca;
-        }
-      }
-      if (clo > -4503599627370496.0 && chi < 4503599627370496.0) {
-        wm.a0 = (long long)ca; wm.a1 = wm.a0; wm.lo = (long long)clo; wm.hi = (long long)chi; wm.hyp = hyp0; wm.pad = 0;
-      } else wm = dot_invalid();
-    } else {
-      if (simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
-      wm = warp_compose(m, lane);
-    }
-    if (piece_dirty) {
-      // keep the 32 leaf maps so that the walker can stitch around the dirty leaves of this piece
-      if (all_simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
-      w.leaf_maps[(int64_t)piece * 32 + lane] = m;
-      if (dirty) {
-        const int slot = atomicAdd(w.dirty_count, 1);
-        if (slot < DOT_MAX_DIRTY) w.dirty_list[slot] = piece * 32 + lane;
-      }
-    }
     // publish the piece map.  The pieces of a chunk belong to this CTA (except at the two ends of its range), so
     // arrivals are counted in shared memory with a CTA-scope fence; only the warp that completes a chunk pays the
     // device-scope fence + ticket of the chunk level.
@@ -405,119 +546,20 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
       dot_publish_chunk_map(w, cm, lane, c, nchunks);
     }
   }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Exact dot, walk phase: one CTA.  (1) sort the dirty leaves, fetch their products; (2) one warp per gap: the
-// <= 9 runs of the gap are loaded at once (one map per lane and run) and collapsed by ordered shuffle scans into
-// ONE map per gap; (3) thread 0 walks  [gap 0][dirty leaf 0][gap 1][dirty leaf 1] ... [gap D]  -- ~2 short steps
-// per dirty leaf.  Any map that fails its check is replayed from global memory in plain floating point, so the
-// result is the serial loop's for every input.
-// ------------------------------------------------------------------------------------------------------
-enum { WALK_THREADS = 512 };
-
-__global__ void __launch_bounds__(WALK_THREADS) k_dot_walk(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
-                                                          DotWork w, CgScalars *sc, int epi, int k,
-                                                          double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
-                                                          const CgScalars *gate, PeerDot pd)
-{
-  pdl_prologue();
-  if (cg_gate_closed(gate, k)) return;
-  __shared__ int dirty[DOT_MAX_DIRTY];
-  __shared__ int sorted[DOT_MAX_DIRTY];
-  __shared__ DotMap gmaps[DOT_MAX_DIRTY + 1];
-  __shared__ double replay_prod[DOT_MAX_DIRTY * DOT_LEAF];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned long long t_begin = (w.stats && tid == 0) ? global_ns() : 0ULL;
-  int slow_gaps = 0;
-  const int D = *w.dirty_count;
-  const long long nleaves = ((n + DOT_PIECE - 1) / DOT_PIECE) * 32;     // whole pieces: the maps that exist
-  double s = 0.0;
-  if (D > DOT_MAX_DIRTY) {                     // pathological input: the literal loop
-    if (tid == 0) s = dot_replay(x, y, 0, n, 0.0);
-  } else {
-    for (int i = tid; i < D; i += WALK_THREADS) dirty[i] = w.dirty_list[i];
-    __syncthreads();
-    for (int i = tid; i < D; i += WALK_THREADS) {        // rank sort (leaf indices are distinct)
-      const int v = dirty[i]; int rk = 0;
-      for (int j = 0; j < D; ++j) rk += dirty[j] < v;
-      sorted[rk] = v;
-    }
-    __syncthreads();
-    // products of the dirty leaves, fetched by all threads at once (the sequential walk then reads smem only)
-    for (int q = tid; q < D * DOT_LEAF; q += WALK_THREADS) {
-      const int64_t i = (int64_t)sorted[q / DOT_LEAF] * DOT_LEAF + (q % DOT_LEAF);
-      replay_prod[q] = i < n ? __dmul_rn(x[i], y[i]) : 0.0;
-    }
-    for (int g = warp; g <= D; g += WALK_THREADS / 32) {
-      const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
-      WalkPiece pc[DOT_GAP_PIECES];
-      dot_gap_decompose(lo, hi, pc);
-      // the maps of the gap in application order form one flat list; lane l takes a contiguous slice of it
-      int total = 0;
-#pragma unroll
-      for (int q = 0; q < DOT_GAP_PIECES; ++q) total += pc[q].count;
-      const int per = (total + 31) / 32, f0 = lane * per, f1 = min(total, f0 + per);
-      DotMap gm = dot_identity();
-      for (int base = f0; base < f1; base += 8) {
-        DotMap buf[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          int f = base + u;
-          if (f < f1) {
-            int q = 0;
-#pragma unroll
-            for (int t = 0; t < DOT_GAP_PIECES - 1; ++t) if (q == t && f >= pc[t].count) { f -= pc[t].count; q = t + 1; }
-            buf[u] = load_map_cg(dot_level_maps(w, pc[q].level) + pc[q].begin + f);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) if (base + u < f1) gm = dot_compose(gm, buf[u]);
-      }
-      gm = warp_compose(gm, lane);
-      if (lane == 31) gmaps[g] = gm;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      for (int g = 0; g <= D; ++g) {
-        const long long lo = g == 0 ? 0 : (long long)sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)sorted[g];
-        if (lo < hi && !dot_apply(gmaps[g], s)) { s = dot_walk_gap_slow(lo, hi, w, x, y, n, s); ++slow_gaps; }
-        if (g < D) {
-          const int64_t b = (int64_t)sorted[g] * DOT_LEAF;
-          const int cnt = (int)(b + DOT_LEAF <= n ? DOT_LEAF : n - b);
-          double pr[DOT_LEAF];
-#pragma unroll
-          for (int i = 0; i < DOT_LEAF; ++i) pr[i] = replay_prod[g * DOT_LEAF + i];
-#pragma unroll
-          for (int i = 0; i < DOT_LEAF; ++i) if (i < cnt) s = __dadd_rn(s, pr[i]);
-        }
-      }
-    }
-  }
+  if (!fold_walk) return;
+  // ---- the CTA that finishes last walks the dirty leaves and the gaps between them (no separate launch) ----
+  __shared__ int walk_here;
+  __threadfence();
+  __syncthreads();
   if (tid == 0) {
-    *w.dirty_count = 0;                         // ready for the next dot on this workspace
-    if (sc) sc->dot_local = s;
-    if (w.stats) {
-      // diagnostics: [0] dots, [1] sum of dirty leaves, [2] max, [3] whole-vector replays, [4] gaps that took the slow path,
-      // [5] total ns in this kernel, [6] max ns, [7] dot index of the max; then a ring of (dirty leaves, ns) per dot
-      const unsigned long long dt = global_ns() - t_begin, idx = w.stats[0];
-      w.stats[0] = idx + 1; w.stats[1] += (unsigned long long)D; if ((unsigned long long)D > w.stats[2]) w.stats[2] = D;
-      if (D > DOT_MAX_DIRTY) w.stats[3] += 1;
-      w.stats[4] += (unsigned long long)slow_gaps; w.stats[5] += dt;
-      if (dt > w.stats[6]) { w.stats[6] = dt; w.stats[7] = idx; }
-      w.stats[DOT_STATS_HEAD + 2 * (idx % DOT_STATS_TRACE)] = ((unsigned long long)slow_gaps << 32) | (unsigned)D;
-      w.stats[DOT_STATS_HEAD + 2 * (idx % DOT_STATS_TRACE) + 1] = dt;
-    }
+    const int t = atomicAdd(w.done_cnt, 1);
+    walk_here = t == (int)gridDim.x - 1;
+    if (walk_here) *w.done_cnt = 0;
   }
-  bool ok = true;
-  if (pd.nranks > 1) s = peer_dot_allreduce(pd, s, ok);     // rank-ordered global sum over NVLink peer memory
-  if (tid == 0) {
-    *w.result = s;
-    if (sc) {
-      if (!ok) { sc->status = CG_COMM_ERROR; sc->stop_iter = -1; }
-      else if (epi != EPI_NONE) cg_epilogue(sc, epi, k, s, normr_hist, rtrans_hist, pap_hist, alpha_hist);
-    }
-  }
+  __syncthreads();
+  if (!walk_here) return;
+  __threadfence();
+  dot_walk_body<NT>(n, x, y, w, wa, *reinterpret_cast<WalkSmem *>(smem));
 }
 
 // the literal serial loop on one device thread (MFE_DOT_SERIAL; validation of the exact dot)
@@ -525,7 +567,6 @@ __global__ void k_dot_serial(int64_t n, const double *__restrict__ x, const doub
                              int epi, int k, double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,
                              const CgScalars *gate)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const double s = dot_replay(x, y, 0, n, 0.0);
   *result = s;
@@ -535,7 +576,6 @@ __global__ void k_dot_serial(int64_t n, const double *__restrict__ x, const doub
 __global__ void k_dot_tree_finish(const double *chunk_prefix, int nchunks, double *result, CgScalars *sc, int epi, int k,
                                   double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist, const CgScalars *gate)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const double s = chunk_prefix[nchunks];
   *result = s;
@@ -545,7 +585,6 @@ __global__ void k_dot_tree_finish(const double *chunk_prefix, int nchunks, doubl
 __global__ void __launch_bounds__(32) k_dot_peer_finish(double *result, CgScalars *sc, int epi, int k, double *normr_hist, double *rtrans_hist,
                                                         double *pap_hist, double *alpha_hist, const CgScalars *gate, PeerDot pd)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   bool ok = true;
   const double g = peer_dot_allreduce(pd, threadIdx.x == 0 ? *result : 0.0, ok);
@@ -561,7 +600,6 @@ __global__ void __launch_bounds__(32) k_dot_peer_finish(double *result, CgScalar
 __global__ void k_dot_allreduce_finish(const double *gathered, int nranks, double *result, CgScalars *sc, int epi, int k,
                                        double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist, const CgScalars *gate)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   double g = gathered[0];
   for (int p = 1; p < nranks; ++p) g = __dadd_rn(g, gathered[p]);

@@ -28,16 +28,6 @@ enum { EPI_NONE = 0, EPI_INIT_RR = 1, EPI_RR = 2, EPI_PAP = 3 };
 
 __device__ __forceinline__ bool cg_gate_closed(const CgScalars *g, int k) { return g != nullptr && k > g->stop_iter; }
 
-// First statement of every CG-loop kernel (see launch_cg in api.cu).  launch_dependents: the next kernel of the
-// stream may start becoming resident once every CTA of this grid has got here; wait: nothing written by the previous
-// kernel (the gate scalars included) is read before that kernel has completed and flushed.  Both are no-ops for a
-// kernel launched without the programmatic-serialization attribute.
-__device__ __forceinline__ void pdl_prologue()
-{
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
 // Scalar bookkeeping after a dot product (dot = the global, rank-ordered value).
 // hist arrays are device arrays of max_iter+1 doubles (may be null).
 __device__ inline void cg_epilogue(CgScalars *s, int epi, int k, double dot, double *normr_hist, double *rtrans_hist,
@@ -211,7 +201,6 @@ __global__ void k_localize_cols(int *__restrict__ cols, int64_t nnz, int start_r
 __global__ void k_pack(const double *__restrict__ x, const int *__restrict__ elements_to_send, int n, double *__restrict__ send_buf,
                        const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) send_buf[i] = x[elements_to_send[i]];
@@ -265,10 +254,11 @@ __device__ __forceinline__ void group_sync(int id, int nthreads)
 struct ScalarArg { const double *ptr; double val; };
 __device__ __forceinline__ double scalar_of(const ScalarArg &a) { return a.ptr ? *a.ptr : a.val; }
 
-__global__ void __launch_bounds__(256) k_waxpby(int64_t n, ScalarArg alpha, const double *__restrict__ x, ScalarArg beta,
-                                                const double *__restrict__ y, double *__restrict__ w, const CgScalars *gate, int k)
+// cg_solve calls this with w aliasing y (p = r + beta*p) and with x aliasing y (p = 1*x + 0*x): no __restrict__; every
+// element is read and then written by the same thread.
+__global__ void __launch_bounds__(256) k_waxpby(int64_t n, ScalarArg alpha, const double *x, ScalarArg beta,
+                                                const double *y, double *w, const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const double a = scalar_of(alpha), bt = scalar_of(beta);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;

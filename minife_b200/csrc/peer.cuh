@@ -64,6 +64,18 @@ __device__ __forceinline__ bool peer_wait_eq(const unsigned long long *p, unsign
     __nanosleep(64);
   }
 }
+// spin until *p >= want (monotone epoch counters: a neighbour may already have published a later epoch); false on timeout
+__device__ __forceinline__ bool peer_wait_ge(const unsigned long long *p, unsigned long long want, unsigned long long timeout_ns)
+{
+  if (ld_acquire_sys_u64(p) >= want) return true;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) if (ld_acquire_sys_u64(p) >= want) return true;
+    if (global_ns() - t0 > timeout_ns) return false;
+    __nanosleep(64);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------
 // halo
@@ -79,7 +91,6 @@ struct PeerHalo {                               // by-value kernel argument
 __global__ void __launch_bounds__(256) k_pack_peer(const double *__restrict__ x, const int *__restrict__ elements_to_send, int nsend,
                                                    PeerHalo ph, unsigned long long epoch, unsigned int *ticket, const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nsend) {
@@ -107,18 +118,22 @@ struct PeerWait {
 // ref/src/exchange_externals.hpp:90-101 + 147-153 (Irecv ... Wait): wait for the neighbours' epoch, then fill the
 // external tail of x.  Few CTAs; every CTA checks all flags itself (no inter-CTA dependency).
 __global__ void __launch_bounds__(256) k_halo_wait_copy(PeerWait pw, unsigned long long epoch, const double *halo, double *__restrict__ x_tail,
-                                                        int n_ext, unsigned long long timeout_ns, int *err, const CgScalars *gate, int k)
+                                                        int n_ext, unsigned long long timeout_ns, int *err, CgScalars *sc, const CgScalars *gate, int k)
 {
-  pdl_prologue();
   if (cg_gate_closed(gate, k)) return;
   __shared__ int bad;
   if (threadIdx.x == 0) bad = 0;
   __syncthreads();
   if (threadIdx.x < pw.n) {
-    if (!peer_wait_eq(pw.flag[threadIdx.x], epoch, timeout_ns)) bad = 1;
+    // epochs are monotone and a neighbour may already be one epoch ahead (its data of that epoch went into the other
+    // buffer): >=, not ==
+    if (!peer_wait_ge(pw.flag[threadIdx.x], epoch, timeout_ns)) bad = 1;
   }
   __syncthreads();
-  if (bad) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
+  if (bad) {                                    // lost peer: close the CG gates at once (the host polls the status word)
+    if (threadIdx.x == 0) { atomicExch(err, 1); if (sc) { sc->status = CG_COMM_ERROR; sc->stop_iter = -1; } }
+    return;
+  }
   __threadfence_system();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_ext; i += gridDim.x * blockDim.x) x_tail[i] = __ldcg(halo + i);
 }

@@ -18,6 +18,7 @@
 // for the exact dot, exact_dot.h -- those values steer speed only, never results).
 #pragma once
 #include "kernels.cuh"
+#include "peer.cuh"
 
 namespace mfe {
 
@@ -44,57 +45,80 @@ __device__ __forceinline__ void dadd_if(double &sum, double prod, int u, int len
 }
 
 // MODE: MV_ALL = every tile in natural order (single GPU, or no overlap); MV_SKIP = natural order, tiles whose
-// tile_base carries MV_SKIP_BIT are skipped (interior pass); MV_LIST = work item i is tile tile_list[i] (boundary pass)
-enum { MV_ALL = 0, MV_SKIP = 1, MV_LIST = 2 };
+// tile_base carries MV_SKIP_BIT are skipped (interior pass); MV_LIST = work item i is tile tile_list[i] (boundary pass);
+// MV_FUSED = the whole multi-rank SpMV in ONE launch: pack my boundary values into the neighbours' halo buffers
+// (ref/src/exchange_externals.hpp:116-137), the MV_SKIP pass while those stores fly, then every warp waits for the
+// neighbours' epoch flags itself and runs its share of the MV_LIST pass, gathering the externals straight from the halo
+// buffer of this epoch (no copy into the tail of x, no second and third launch).
+enum { MV_ALL = 0, MV_SKIP = 1, MV_LIST = 2, MV_FUSED = 3 };
 
-template <int G, int S, int H, int MODE>
-__global__ void __launch_bounds__(32 * G, 1)
-k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const uint32_t *__restrict__ roff,
-         const int64_t *__restrict__ tile_base, const double *__restrict__ x, double *__restrict__ y, int64_t nrows,
-         int64_t ntiles, int64_t nnz_padded, int zmask, double *__restrict__ piece_sums, double *__restrict__ chunk_sums,
-         const CgScalars *gate, int k, const int *__restrict__ tile_list, int64_t nwork, int ell_width)
+struct MvArgs {                      // by-value kernel argument
+  const double *coefs; const int *cols; const uint32_t *roff;
+  const int64_t *tile_base;          // 64-bit nnz offset of every tile (ntiles + 1)
+  const int64_t *tile_base_flagged;  // same with MV_SKIP_BIT on the tiles that reference externals (MV_SKIP / MV_FUSED)
+  const double *x; double *y;
+  int64_t nrows, ntiles, nnz_padded;
+  int zmask;                         // always 0 at run time (see the gather batches)
+  double *piece_sums, *chunk_sums;   // p.Ap prediction sums (null: none)
+  const CgScalars *gate; int k;
+  const int *tile_list; int64_t nlist;   // MV_LIST / MV_FUSED: the boundary tiles
+  int ell_width;
+  int seed_y;                        // 1: the caller's y is meaningful (API call): beta*y[row] is formed for every row
+  // MV_FUSED only
+  const double *halo;                // externals of this epoch: column c >= nrows reads halo[c - nrows]
+  const int *elements_to_send; int nsend;
+  PeerHalo ph; PeerWait pw;
+  unsigned long long epoch, timeout_ns;
+  unsigned int *ticket; int *err; CgScalars *sc;
+};
+
+// x[col]; EXT: columns >= nrows are externals in the halo buffer, which the neighbours write while this kernel runs
+// (L2 loads: L1 may still hold the buffer's lines from two epochs ago)
+template <bool EXT>
+__device__ __forceinline__ double mv_x(const MvArgs &a, int col)
 {
-  // ell_width > 0: the matrix stands for the reference's ELLMatrix (ref/src/ELLMatrix.hpp), whose matvec
-  // (SparseMatrix_functions.hpp:580-613) walks ell_width entries in every row: a row with fewer real entries ends with
-  // padding entries (coef 0.0, col 0), i.e. with (ell_width - len) additions of 0.0 * x[0].  Reproduced literally (they
-  // decide the sign of a zero result and propagate a non-finite x[0]), on the ragged path only.
-  // Programmatic dependent launch: everything up to griddepcontrol.wait below touches only the matrix (static
-  // during a solve), so the first tiles are already streaming in while the previous kernel (the p update) drains.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  // tile_list == nullptr: all tiles 0 .. ntiles-1 (nwork == ntiles).  Otherwise work item i is tile tile_list[i]
-  // (the boundary tiles of a rank, after the halo arrived).  The interior pass that overlaps the halo exchange runs
-  // over all tiles in natural order with a FLAGGED copy of tile_base: bit 62 of tile_base[t] set = skip tile t
-  // (it references external columns), so the flag costs no extra load on the TMA issue path.
+  if (EXT && col >= (int)a.nrows) return __ldcg(a.halo + (col - (int)a.nrows));
+  return __ldg(a.x + col);
+}
+
+struct MvSmem {
+  unsigned char *gbase;    // this warp's stages
+  uint64_t *bars;          // this warp's mbarriers
+  double *racc; int *rcnt; volatile int *rtag;   // ring of round sums (G == 16)
+};
+
+// One pass over the work items of this CTA.  PASS is MV_ALL, MV_SKIP or MV_LIST; EXT: externals come from a.halo.
+// Returns false when the gate was closed (nothing was computed).
+template <int G, int S, int H, int PASS, bool EXT>
+__device__ __forceinline__ bool mv_pass(const MvArgs &a, const MvSmem &sm, uint32_t &phase_bits, uint64_t pol_stream, bool check_gate)
+{
   constexpr int TR = MV_TILE_ROWS;
   constexpr int CAP = MatvecCfg::CAP;
   constexpr int SLOT = MatvecCfg::SLOT_BYTES;
   constexpr int U = 27;                               // one pass covers a whole stencil row
   constexpr int B = (U + H - 1) / H;                  // entries per gather batch
-  extern __shared__ __align__(128) unsigned char smem[];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned char *gbase = smem + (size_t)w * S * SLOT;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
-  double *racc = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + (size_t)G * S * 8);     // [8] round sums (G == 16)
-  int *rcnt = reinterpret_cast<int *>(racc + 8);                                                  // [8] round arrivals
-  volatile int *rtag = rcnt + 8;                                                                  // [8] round each slot collects
-  uint64_t pol_stream = 0;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  const int64_t *__restrict__ tile_base = PASS == MV_SKIP ? a.tile_base_flagged : a.tile_base;
+  const int64_t nwork = PASS == MV_LIST ? a.nlist : a.ntiles;
+  const int64_t nrows = a.nrows, ntiles = a.ntiles, nnz_padded = a.nnz_padded;
+  const double *__restrict__ coefs = a.coefs; const int *__restrict__ cols = a.cols; const uint32_t *__restrict__ roff = a.roff;
+  double *__restrict__ piece_sums = a.piece_sums, *__restrict__ chunk_sums = a.chunk_sums;
   // Round jj of this CTA covers the work items first .. first + G - 1, first = (blockIdx.x + jj * gridDim.x) * G; warp w
   // takes item first + w, which is tile first + w (MV_ALL), tile_list[first + w] (MV_LIST), or -- MV_SKIP -- tile
   // first + (w + jj) % G: the rotation spreads the skipped tiles over the warps (the boundary tiles of an x-split box
   // recur with period 8 in the tile index, which a fixed warp <-> residue assignment would turn into idle warps).
   auto item = [&](int64_t jj, int64_t &t) -> bool {
     const int64_t first = ((int64_t)blockIdx.x + jj * (int64_t)gridDim.x) * G;
-    if (MODE == MV_LIST) {
+    if (PASS == MV_LIST) {
       const int64_t i = first + w;
       if (i >= nwork) return false;
-      t = (int64_t)tile_list[i];
+      t = (int64_t)a.tile_list[i];
       return true;
     }
-    t = first + (MODE == MV_SKIP ? (int64_t)((w + (int)(jj % G)) % G) : (int64_t)w);
+    t = first + (PASS == MV_SKIP ? (int64_t)((w + (int)(jj % G)) % G) : (int64_t)w);
     return t < ntiles;
   };
-  constexpr int64_t SKIP = MODE == MV_SKIP ? MV_SKIP_BIT : 0;
+  constexpr int64_t SKIP = PASS == MV_SKIP ? MV_SKIP_BIT : 0;
 
   auto issue = [&](int64_t t, int s) -> bool {
     const int64_t b0 = tile_base[t];
@@ -104,32 +128,23 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     if (a1 > nnz_padded) a1 = nnz_padded;
     const int64_t n = a1 - a0;
     if (n <= 0 || n > CAP) return false;                // oversized tile: consumers read global memory directly
-    double *sc = reinterpret_cast<double *>(gbase + (size_t)s * SLOT);
-    int *si = reinterpret_cast<int *>(gbase + (size_t)s * SLOT + CAP * 8);
-    mbar_expect_tx(&bars[s], (uint32_t)(n * 12));
-    bulk_g2s_hint(sc, coefs + a0, (uint32_t)(n * 8), &bars[s], pol_stream);
-    bulk_g2s_hint(si, cols + a0, (uint32_t)(n * 4), &bars[s], pol_stream);
+    double *sc = reinterpret_cast<double *>(sm.gbase + (size_t)s * SLOT);
+    int *si = reinterpret_cast<int *>(sm.gbase + (size_t)s * SLOT + CAP * 8);
+    mbar_expect_tx(&sm.bars[s], (uint32_t)(n * 12));
+    bulk_g2s_hint(sc, coefs + a0, (uint32_t)(n * 8), &sm.bars[s], pol_stream);
+    bulk_g2s_hint(si, cols + a0, (uint32_t)(n * 4), &sm.bars[s], pol_stream);
     return true;
   };
-
-  if (lane == 0) {
-    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (threadIdx.x < 8) { racc[threadIdx.x] = 0.0; rcnt[threadIdx.x] = 0; rtag[threadIdx.x] = (int)threadIdx.x; }
-  __syncthreads();
 
   unsigned armed0 = 0;
   if (lane == 0)
     for (int s = 0; s < S; ++s) { int64_t ti; if (item(s, ti) && issue(ti, s)) armed0 |= 1u << s; }
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // from here on x, y, the gate scalars and the sums may be touched
-  if (cg_gate_closed(gate, k)) {                        // iteration switched off: let the copies in flight land, then leave
+  if (check_gate && cg_gate_closed(a.gate, a.k)) {      // iteration switched off: let the copies in flight land, then leave
     if (lane == 0)
-      for (int s = 0; s < S; ++s) if ((armed0 >> s) & 1u) mbar_wait(&bars[s], 0);
-    return;
+      for (int s = 0; s < S; ++s) if ((armed0 >> s) & 1u) mbar_wait(&sm.bars[s], (phase_bits >> s) & 1u);
+    return false;
   }
 
-  uint32_t phase_bits = 0;            // expected mbarrier parity per stage (flips each time a stage completes)
   // software-pipelined row offsets: (o0,o1) of this lane's row in the NEXT tile are loaded one tile ahead
   uint32_t o0n = 0, o1n = 0; int64_t tb0n = 0, tb1n = 0;
   int64_t tnext = 0;
@@ -167,28 +182,33 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
     const int len = live ? (int)(o1 - o0) : 0;
     const bool full = staged && __all_sync(0xffffffffu, len == U);
 
-    double sum = 0.0;                 // beta*y with beta = 0 (SparseMatrix_functions.hpp:565-568)
-    const double xr = (piece_sums && live) ? __ldg(x + r) : 0.0;
+    // The reference starts every row from beta*y[row] with beta = 0 (SparseMatrix_functions.hpp:565-568): +0.0 or -0.0 for
+    // a finite y[row].  Here the entries are summed onto -0.0, the additive identity ((-0) + t = t for EVERY t, zeros of
+    // either sign included), and the seed is added last: fl(0*y[row] + S) equals the reference's ((0*y + t1) + t2) + ...
+    // bit for bit -- a nonzero S absorbs a zero seed, a zero S is -0.0 exactly when every term was -0.0, and a non-finite
+    // y[row] makes both NaN.  So y[row] only has to be read when S is -0.0 (or always, for an API call: a.seed_y).
+    double sum = -0.0;
+    const double xr = (piece_sums && live) ? __ldg(a.x + r) : 0.0;
     if (staged) {
-      mbar_wait(&bars[s], parity);
+      mbar_wait(&sm.bars[s], parity);
       phase_bits ^= 1u << s;
-      const double *sc = reinterpret_cast<const double *>(gbase + (size_t)s * SLOT);
-      const int *si = reinterpret_cast<const int *>(gbase + (size_t)s * SLOT + CAP * 8);
+      const double *sc = reinterpret_cast<const double *>(sm.gbase + (size_t)s * SLOT);
+      const int *si = reinterpret_cast<const int *>(sm.gbase + (size_t)s * SLOT + CAP * 8);
       // first entry of this row inside the stage: 32-bit difference to the tile's first row + tile skew
       const int base = (int)(uint32_t)(o0 - (uint32_t)tb0) + (int)(tb0 - a0);
       if (full) {
         // All gathers of a batch must be in flight before its dependent add chain starts (the SM issues in order:
         // an add placed between the loads would serialise them).  Fold a bit of every gathered value into a token
-        // that is masked to zero at run time (zmask == 0) and seed the chain with it: + 0.0, exact.
+        // that is masked to zero at run time (zmask == 0) and seed the chain with it: + (-0.0), the exact identity.
 #pragma unroll
         for (int h = 0; h < H; ++h) {
           double cv[B], xv[B];
 #pragma unroll
-          for (int u = 0; u < B; ++u) if (h * B + u < U) { cv[u] = sc[base + h * B + u]; xv[u] = __ldg(x + si[base + h * B + u]); }
+          for (int u = 0; u < B; ++u) if (h * B + u < U) { cv[u] = sc[base + h * B + u]; xv[u] = mv_x<EXT>(a, si[base + h * B + u]); }
           unsigned tok = 0;
 #pragma unroll
           for (int u = 0; u < B; ++u) if (h * B + u < U) tok |= (unsigned)__double2hiint(xv[u]);
-          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+          sum = __dadd_rn(sum, __hiloint2double((int)((tok & (unsigned)a.zmask) | 0x80000000u), 0));
 #pragma unroll
           for (int u = 0; u < B; ++u) if (h * B + u < U) sum = __dadd_rn(sum, __dmul_rn(cv[u], xv[u]));
         }
@@ -199,30 +219,31 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
           for (int u = 0; u < B; ++u) {
             const int ii = (i0 + u < len) ? base + i0 + u : base;
             cv[u] = sc[ii];
-            xv[u] = __ldg(x + si[ii]);
+            xv[u] = mv_x<EXT>(a, si[ii]);
           }
           unsigned tok = 0;
 #pragma unroll
           for (int u = 0; u < B; ++u) tok |= (unsigned)__double2hiint(xv[u]);
-          sum = __dadd_rn(sum, __hiloint2double((int)(tok & (unsigned)zmask), 0));
+          sum = __dadd_rn(sum, __hiloint2double((int)((tok & (unsigned)a.zmask) | 0x80000000u), 0));
 #pragma unroll
           for (int u = 0; u < B; ++u) dadd_if(sum, __dmul_rn(cv[u], xv[u]), i0 + u, len);
         }
-        if (len < ell_width) {
-          const double pad = __dmul_rn(0.0, __ldg(x));
-          for (int u = len; u < ell_width; ++u) sum = __dadd_rn(sum, pad);
+        if (len < a.ell_width) {
+          const double pad = __dmul_rn(0.0, __ldg(a.x));
+          for (int u = len; u < a.ell_width; ++u) sum = __dadd_rn(sum, pad);
         }
       }
-    } else if (live) {
+    } else if (live) {                // oversized tile: straight from global memory
       const int64_t b0 = tb0 + (int64_t)(uint32_t)(o0 - (uint32_t)tb0);
-      for (int64_t i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[b0 + i], __ldg(x + cols[b0 + i])));
-      if (len < ell_width) {
-        const double pad = __dmul_rn(0.0, __ldg(x));
-        for (int u = len; u < ell_width; ++u) sum = __dadd_rn(sum, pad);
+      for (int64_t i = 0; i < len; ++i) sum = __dadd_rn(sum, __dmul_rn(coefs[b0 + i], mv_x<EXT>(a, cols[b0 + i])));
+      if (len < a.ell_width) {
+        const double pad = __dmul_rn(0.0, __ldg(a.x));
+        for (int u = len; u < a.ell_width; ++u) sum = __dadd_rn(sum, pad);
       }
     }
+    if (live && (a.seed_y || __double_as_longlong(sum) == (long long)0x8000000000000000ULL)) sum = __dadd_rn(__dmul_rn(0.0, a.y[r]), sum);
     double prod = 0.0;
-    if (live) { y[r] = sum; prod = xr * sum; }
+    if (live) { a.y[r] = sum; prod = xr * sum; }
     if (piece_sums) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) prod += __shfl_down_sync(0xffffffffu, prod, o);
@@ -232,27 +253,30 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
       int64_t t2;
       if (item(j + S, t2)) issue(t2, s);
       if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
-        if (G == 16 && MODE != MV_LIST) {
+        if (G == 16 && PASS != MV_LIST) {
           // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
           // rounds; the warp that completes a round publishes it and hands the slot to round j + 8).  A warp that is
           // 8 rounds ahead of a straggler waits for the slot (the straggler never waits for a later round, so this
           // cannot deadlock): the sums must be exact per piece -- a sum that leaks into the wrong piece shifts the
           // predicted running sum by ~1e-6 relative, the dot then meets binade crossings where it expects none and
           // falls into its slow path (measured: 50-80 ms per p.Ap dot at 512^3).
-          const int slot = (int)(j & 7);
+          const int64_t jr = j;
+          const int slot = (int)(jr & 7);
           const int64_t first = ((int64_t)blockIdx.x + j * (int64_t)gridDim.x) * G;   // first tile of the round
           const int expect = (int)(ntiles - first < G ? ntiles - first : G);
-          while (rtag[slot] != (int)j) { }
+          while (sm.rtag[slot] != (int)jr) { }
           __threadfence_block();
-          atomicAdd(&racc[slot], prod);
+          atomicAdd(&sm.racc[slot], prod);
           __threadfence_block();
-          if (atomicAdd(&rcnt[slot], 1) == expect - 1) {
+          if (atomicAdd(&sm.rcnt[slot], 1) == expect - 1) {
             __threadfence_block();
-            const double v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(&racc[slot]), 0ULL));
-            rcnt[slot] = 0;
+            const double v = __longlong_as_double((long long)atomicExch(reinterpret_cast<unsigned long long *>(&sm.racc[slot]), 0ULL));
+            sm.rcnt[slot] = 0;
             __threadfence_block();
-            rtag[slot] = (int)j + 8;
-            piece_sums[first >> 4] = v;
+            sm.rtag[slot] = (int)jr + 8;
+            // MV_ALL owns the piece (plain store); the interior pass shares it with the boundary pass, which may run
+            // earlier on another CTA of a fused launch (both add into sums that the previous k_xr_update zeroed)
+            if (PASS == MV_ALL) piece_sums[first >> 4] = v; else atomicAdd(&piece_sums[first >> 4], v);
             atomicAdd(&chunk_sums[first >> 7], v);
           }
         } else {
@@ -262,6 +286,79 @@ k_matvec(const double *__restrict__ coefs, const int *__restrict__ cols, const u
       }
     }
   }
+  return true;
+}
+
+template <int G, int S, int H, int MODE>
+__global__ void __launch_bounds__(32 * G, 1)
+k_matvec(const __grid_constant__ MvArgs a)
+{
+  // ell_width > 0: the matrix stands for the reference's ELLMatrix (ref/src/ELLMatrix.hpp), whose matvec
+  // (SparseMatrix_functions.hpp:580-613) walks ell_width entries in every row: a row with fewer real entries ends with
+  // padding entries (coef 0.0, col 0), i.e. with (ell_width - len) additions of 0.0 * x[0].  Reproduced literally (they
+  // decide the sign of a zero result and propagate a non-finite x[0]), on the ragged path only.
+  constexpr int SLOT = MatvecCfg::SLOT_BYTES;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  MvSmem sm;
+  sm.gbase = smem + (size_t)w * S * SLOT;
+  sm.bars = reinterpret_cast<uint64_t *>(smem + (size_t)G * S * SLOT) + w * S;
+  sm.racc = reinterpret_cast<double *>(smem + (size_t)G * S * SLOT + (size_t)G * S * 8);     // [8] round sums (G == 16)
+  sm.rcnt = reinterpret_cast<int *>(sm.racc + 8);                                             // [8] round arrivals
+  sm.rtag = sm.rcnt + 8;                                                                      // [8] round each slot collects
+  int *flag_last = const_cast<int *>(sm.rtag) + 8;
+  uint64_t pol_stream = 0;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  if (lane == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&sm.bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 8) { sm.racc[threadIdx.x] = 0.0; sm.rcnt[threadIdx.x] = 0; sm.rtag[threadIdx.x] = (int)threadIdx.x; }
+  __syncthreads();
+  uint32_t phase_bits = 0;            // expected mbarrier parity per stage (flips each time a stage completes)
+
+  if (MODE != MV_FUSED) {
+    mv_pass<G, S, H, MODE, false>(a, sm, phase_bits, pol_stream, true);
+    return;
+  }
+  // ---- MV_FUSED ----
+  if (cg_gate_closed(a.gate, a.k)) return;             // uniform over the grid: nobody packs, nobody waits
+  // (1) pack: ref/src/exchange_externals.hpp:116-137 as stores into the neighbours' halo buffers of this epoch; the last
+  //     CTA to finish (ticket) publishes the epoch into the neighbours' flags
+  if (a.ph.n > 0) {
+    const int nthr = (int)(gridDim.x * blockDim.x);
+    for (int i = (int)(blockIdx.x * blockDim.x + threadIdx.x); i < a.nsend; i += nthr) {
+      int s = 0;
+#pragma unroll 1
+      while (s + 1 < a.ph.n && i >= a.ph.start[s + 1]) ++s;
+      a.ph.dst[s][i - a.ph.start[s]] = a.x[a.elements_to_send[i]];
+    }
+    __threadfence_system();                             // my stores are ordered before the ticket below, system wide
+    __syncthreads();
+    if (threadIdx.x == 0) *flag_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (*flag_last) {
+      __threadfence_system();                           // the other CTAs' stores (observed through the ticket) before the flags
+      if ((int)threadIdx.x < a.ph.n) st_release_sys_u64(a.ph.flag[threadIdx.x], a.epoch);
+      if (threadIdx.x == 0) *a.ticket = 0u;
+    }
+  }
+  // (2) the tiles that need no external
+  mv_pass<G, S, H, MV_SKIP, false>(a, sm, phase_bits, pol_stream, false);
+  if (a.nlist <= 0) return;
+  // (3) Irecv ... Wait (exchange_externals.hpp:90-101, 147-153): every warp checks the neighbours' flags itself
+  if (a.pw.n > 0) {
+    bool ok = true;
+    if (lane < a.pw.n) ok = peer_wait_ge(a.pw.flag[lane], a.epoch, a.timeout_ns);
+    ok = __all_sync(0xffffffffu, ok);
+    __syncwarp();
+    if (!ok) {
+      if (lane == 0) { atomicExch(a.err, 1); if (a.sc) { a.sc->status = CG_COMM_ERROR; a.sc->stop_iter = -1; } }
+      return;
+    }
+  }
+  // (4) the boundary tiles (their prediction sums go through atomics, not through the ring of round sums)
+  mv_pass<G, S, H, MV_LIST, true>(a, sm, phase_bits, pol_stream, false);
 }
 
 // Streaming probe (measurement only): the staging half of k_matvec with the consumer removed -- every warp waits

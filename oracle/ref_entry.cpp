@@ -20,6 +20,7 @@
 #include <limits>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 #ifdef HAVE_MPI
 #include <mpi.h>
@@ -366,6 +367,38 @@ void dumpv(const std::string& dir, const char* name, int np, int rank, const cha
 {
   dump(dir, name, np, rank, ext, v.empty() ? (const T*)0 : &v[0], v.size());
 }
+// CRC-32 (IEEE 802.3 / zlib polynomial, reflected) -- equals Python's zlib.crc32 over the array's bytes
+unsigned crc32_bytes(const unsigned char* p, size_t n)
+{
+  static unsigned table[8][256];
+  static bool init = false;
+  if (!init) {
+    for (unsigned i = 0; i < 256; ++i) {
+      unsigned c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+      table[0][i] = c;
+    }
+    for (unsigned i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xff];
+    init = true;
+  }
+  unsigned c = 0xFFFFFFFFu;
+  while (n >= 8) {                      // slicing-by-8
+    unsigned lo, hi;
+    std::memcpy(&lo, p, 4); std::memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xff] ^ table[6][(lo >> 8) & 0xff] ^ table[5][(lo >> 16) & 0xff] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xff] ^ table[2][(hi >> 8) & 0xff] ^ table[1][(hi >> 16) & 0xff] ^ table[0][hi >> 24];
+    p += 8; n -= 8;
+  }
+  while (n--) c = table[0][(c ^ *p++) & 0xff] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+template <typename T>
+unsigned crc_of(const std::vector<T>& v)
+{
+  return crc32_bytes(v.empty() ? (const unsigned char*)0 : reinterpret_cast<const unsigned char*>(&v[0]), v.size() * sizeof(T));
+}
 }
 
 int main(int argc, char** argv)
@@ -378,6 +411,11 @@ int main(int argc, char** argv)
   int max_iter = argc > 5 ? std::atoi(argv[5]) : 200;
   float load_imbalance = argc > 6 ? (float)std::atof(argv[6]) : 0.0f;
 
+  // REF_DUMP_LEAN=1: large meshes -- no array dumps; CRC-32 (zlib polynomial) of every array instead, the index maps,
+  // and the four per-iteration histories.  Same pipeline, same order of calls.
+  const bool lean = std::getenv("REF_DUMP_LEAN") != 0 && std::atoi(std::getenv("REF_DUMP_LEAN")) != 0;
+  std::vector<unsigned> crcs;
+
   RefProblem* P = make_problem(nx, ny, nz, numprocs, myproc);
   if (load_imbalance > 0) {      // ref/src/driver.hpp:137-139, then the mesh is (re)built from the changed box
     YAML_Doc ydoc("miniFE", "dump");
@@ -388,21 +426,34 @@ int main(int argc, char** argv)
   }
   { CoutCapture quiet; miniFE::generate_matrix_structure(*P->mesh, P->A); }
   make_vectors(P);
-  dumpv(dir, "rows", numprocs, myproc, "i32", P->A.rows);
-  dumpv(dir, "row_offsets", numprocs, myproc, "i32", P->A.row_offsets);
-  dumpv(dir, "cols_global", numprocs, myproc, "i32", P->A.packed_cols);
   dump(dir, "box", numprocs, myproc, "i32", P->my_box.ranges, 6);
+  if (lean) {
+    crcs.push_back(crc_of(P->A.row_offsets)); crcs.push_back(crc_of(P->A.packed_cols));
+  } else {
+    dumpv(dir, "rows", numprocs, myproc, "i32", P->A.rows);
+    dumpv(dir, "row_offsets", numprocs, myproc, "i32", P->A.row_offsets);
+    dumpv(dir, "cols_global", numprocs, myproc, "i32", P->A.packed_cols);
+  }
   ref_assemble_FE_data(P);
-  dumpv(dir, "coefs_prebc", numprocs, myproc, "f64", P->A.packed_coefs);
-  dumpv(dir, "b_prebc", numprocs, myproc, "f64", P->b->coefs);
+  if (lean) { crcs.push_back(crc_of(P->A.packed_coefs)); crcs.push_back(crc_of(P->b->coefs)); }
+  else {
+    dumpv(dir, "coefs_prebc", numprocs, myproc, "f64", P->A.packed_coefs);
+    dumpv(dir, "b_prebc", numprocs, myproc, "f64", P->b->coefs);
+  }
   ref_impose_dirichlet(P, 0);
   ref_impose_dirichlet(P, 1);
-  dumpv(dir, "coefs", numprocs, myproc, "f64", P->A.packed_coefs);
-  dumpv(dir, "b", numprocs, myproc, "f64", P->b->coefs);
+  if (lean) { crcs.push_back(crc_of(P->A.packed_coefs)); crcs.push_back(crc_of(P->b->coefs)); }
+  else {
+    dumpv(dir, "coefs", numprocs, myproc, "f64", P->A.packed_coefs);
+    dumpv(dir, "b", numprocs, myproc, "f64", P->b->coefs);
+  }
   ref_make_local_matrix(P);
-  dumpv(dir, "cols_local", numprocs, myproc, "i32", P->A.packed_cols);
+  if (lean) crcs.push_back(crc_of(P->A.packed_cols));
+  else dumpv(dir, "cols_local", numprocs, myproc, "i32", P->A.packed_cols);
   int num_cols = P->A.num_cols;
   dump(dir, "num_cols", numprocs, myproc, "i32", &num_cols, 1);
+  long long sizes[2] = { (long long)P->A.rows.size(), (long long)P->A.packed_cols.size() };
+  dump(dir, "sizes", numprocs, myproc, "i64", sizes, 2);
 #ifdef HAVE_MPI
   dumpv(dir, "external_index", numprocs, myproc, "i32", P->A.external_index);
   dumpv(dir, "external_local_index", numprocs, myproc, "i32", P->A.external_local_index);
@@ -419,9 +470,14 @@ int main(int argc, char** argv)
     nh.resize(iters + 1); rh.resize(iters + 1); ph.resize(iters + 1); ah.resize(iters + 1);
     dumpv(dir, "normr_hist", numprocs, myproc, "f64", nh);
     dumpv(dir, "pap_hist", numprocs, myproc, "f64", ph);
-    dumpv(dir, "x", numprocs, myproc, "f64", P->x->coefs);
+    dumpv(dir, "rtrans_hist", numprocs, myproc, "f64", rh);
+    dumpv(dir, "alpha_hist", numprocs, myproc, "f64", ah);
+    if (lean) crcs.push_back(crc_of(P->x->coefs));
+    else dumpv(dir, "x", numprocs, myproc, "f64", P->x->coefs);
     if (myproc == 0) std::cout << "np=" << numprocs << " iters=" << iters << " normr=" << normr << std::endl;
   }
+  // order: row_offsets, cols_global, coefs_prebc, b_prebc, coefs, b, cols_local, x
+  if (lean) dumpv(dir, "crc", numprocs, myproc, "u32", crcs);
   delete P;
   miniFE::finalize_mpi();
   return 0;

@@ -26,8 +26,13 @@ def main():
     from oracle_lib import Oracle, EPS
     ap = argparse.ArgumentParser()
     ap.add_argument("--sizes", default="2x2x2,8x8x8,5x3x7,20x30x40,64x64x64")
-    ap.add_argument("--modes", default="peer+overlap,peer,nccl", help="communication modes to check: peer+overlap (NVLink peer stores, "
-                    "interior SpMV overlapped), peer (no overlap), nccl (send/recv + allgather)")
+    ap.add_argument("--modes", default="peer+overlap,peer+overlap2,peer,nccl", help="communication modes to check: peer+overlap (NVLink peer "
+                    "stores, ONE fused SpMV launch: pack, interior tiles, flag wait, boundary tiles), peer+overlap2 (the same as four "
+                    "launches), peer (no overlap), nccl (send/recv + allgather)")
+    ap.add_argument("--big", default="", help="comma-separated tests/golden/big_*.npz files (np must equal the world size): the run is "
+                    "compared with the UNMODIFIED reference's record at that size -- CRC-32 of every array after every phase, the index "
+                    "maps, the four per-iteration histories and the solution -- instead of with the in-process oracle")
+    ap.add_argument("--big-modes", default="peer+overlap")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -67,7 +72,7 @@ def main():
         dist.broadcast(idt, 0)
         mesh.comm_init(bytes(idt.cpu().numpy().tobytes()))
         mesh.set_option("comm_mode", 0 if mode == "nccl" else 1)
-        mesh.set_option("overlap", 1 if mode == "peer+overlap" else 0)
+        mesh.set_option("overlap", {"peer+overlap": 1, "peer+overlap2": 2}.get(mode, 0))
         size = "%s[%s]" % (size, mode)
         A = mf.CSRMatrix()
         mf.generate_matrix_structure(mesh, A)
@@ -113,9 +118,63 @@ def main():
         vrc, vmax, _ = mf.verify_solution(mesh, None, 0.06, whole, info=True)
         wrc, wmax, _ = o.verify_solution(0.06, whole, info=True)
         check(vrc == wrc and abs(vmax - wmax) <= 1e-12 * max(wmax, 1e-30) + 1e-15, "%s verify_solution %r vs %r" % (size, (vrc, vmax), (wrc, wmax)))
+        # time_kernels (ref/src/time_kernels.hpp:97-124): back-to-back matvecs with no dot between them -- consecutive halo
+        # epochs with nothing that re-synchronises the ranks (a neighbour may run one epoch ahead)
+        xk = mf.Vector(first, A.num_rows()); xk.coefs[:] = f(first + np.arange(A.num_rows()))
+        nk = 6
+        xdotp, _ = mf.time_kernels(A, b, xk, None, nk)
+        wx, wxdotp = o.time_kernels(f, nk)
+        check(np.array_equal(bits(xk.coefs), bits(wx[rank])) and bits(np.array([xdotp]))[0] == bits(np.array([wxdotp]))[0], "%s time_kernels" % size)
         if rank == 0:
             rel = np.abs(h["normr"][:k + 1] - want["normr"][:k + 1]) / np.maximum(want["normr"][:k + 1], 1e-300)
             print("size %s np=%d: iters %d (oracle %d), final resid %.6g, max rel diff of history %.3g" % (size, world, iters, want["num_iters"], normr, rel.max()), flush=True)
+        mesh.close()
+
+    # ---- large sizes: against the unmodified reference's golden record (tests/golden/make_big_golden.py) ----
+    import zlib
+    crc = lambda a: np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
+    for path, mode in [(p_, m_) for p_ in args.big.split(",") if p_ for m_ in args.big_modes.split(",")]:
+        g = np.load(path)
+        if int(g["np"]) != world:
+            continue
+        n = tuple(int(v) for v in g["n"])
+        tag = "%s[%s]" % (os.path.basename(path)[:-4], mode)
+        gbox = mf.Box([0, n[0], 0, n[1], 0, n[2]])
+        boxes = mf.box_partition(0, world, 2, gbox)
+        check(np.array_equal(boxes[rank].ranges, g["box_%d" % rank]), "%s box" % tag)
+        mesh = mf.simple_mesh_description(gbox, boxes[rank], rank=rank, nranks=world, all_boxes=boxes, device=local)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(mf.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        mesh.comm_init(bytes(idt.cpu().numpy().tobytes()))
+        mesh.set_option("comm_mode", 0 if mode == "nccl" else 1)
+        mesh.set_option("overlap", {"peer+overlap": 1, "peer+overlap2": 2}.get(mode, 0))
+        A = mf.CSRMatrix()
+        mf.generate_matrix_structure(mesh, A)
+        nrows, nnz = A.num_rows(), A.num_nonzeros()
+        check((nrows, nnz) == tuple(int(v) for v in g["sizes_%d" % rank]), "%s sizes" % tag)
+        b = mf.Vector(int(A.rows[0]), nrows); x = mf.Vector(int(A.rows[0]), nrows)
+        check(crc(A.row_offsets) == g["crc_row_offsets_%d" % rank] and crc(A.packed_cols) == g["crc_cols_global_%d" % rank], "%s structure CRC" % tag)
+        mf.assemble_FE_data(mesh, A, b)
+        check(crc(A.packed_coefs) == g["crc_coefs_prebc_%d" % rank] and crc(b.coefs) == g["crc_b_prebc_%d" % rank], "%s assembled A/b CRC" % tag)
+        mf.impose_dirichlet(0.0, A, b, bc_rows=0); mf.impose_dirichlet(1.0, A, b, bc_rows=1)
+        check(crc(A.packed_coefs) == g["crc_coefs_%d" % rank] and crc(b.coefs) == g["crc_b_%d" % rank], "%s A/b after Dirichlet CRC" % tag)
+        mf.make_local_matrix(A)
+        check(crc(A.packed_cols) == g["crc_cols_local_%d" % rank] and A.num_cols == int(g["num_cols_%d" % rank]), "%s local columns CRC" % tag)
+        for m in ("neighbors", "recv_length", "send_length"):
+            check(np.array_equal(getattr(A, m), g["%s_%d" % (m, rank)]), "%s %s" % (tag, m))
+        for m in ("external_index", "external_local_index", "elements_to_send"):
+            a = getattr(A, m)
+            check(len(a) == int(g["len_%s_%d" % (m, rank)]) and crc(a) == g["crc_%s_%d" % (m, rank)], "%s %s CRC" % (tag, m))
+        iters, normr, times, h = mf.cg_solve(A, b, x, mf.matvec_std(), 200, EPS, history=True)
+        check(iters == len(g["normr"]) - 1, "%s iterations %d vs %d" % (tag, iters, len(g["normr"]) - 1))
+        k = min(iters, len(g["normr"]) - 1)
+        for name in ("normr", "rtrans", "pap", "alpha"):
+            check(np.array_equal(bits(h[name][1 if name in ("pap", "alpha") else 0:k + 1]), bits(g[name][1 if name in ("pap", "alpha") else 0:k + 1])), "%s %s history" % (tag, name))
+        check(crc(x.coefs) == g["crc_x_%d" % rank], "%s solution CRC" % tag)
+        if rank == 0:
+            print("big %s np=%d: iters %d, final resid %.17g (golden %.17g)" % (tag, world, iters, h["normr"][k], g["normr"][k]), flush=True)
         mesh.close()
     t = torch.tensor([len(failures)], device="cuda")
     dist.all_reduce(t)

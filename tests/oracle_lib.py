@@ -183,10 +183,34 @@ class Oracle:
             self.L.mfo_get_map(self.h, r, name.encode(), _ptr(o))
         return o
 
-    def matvec(self, x, r=0):
-        y = np.zeros(self.nrows(r))
+    def matvec(self, x, r=0, y0=None):
+        """y0: the stale contents of y (the reference forms beta*y[row] with beta = 0, SparseMatrix_functions.hpp:565)"""
+        y = np.zeros(self.nrows(r)) if y0 is None else np.array(y0, np.float64)
         self.L.mfo_matvec(self.h, r, np.ascontiguousarray(x, np.float64), y)
         return y
+
+    def time_kernels(self, f, max_iter):
+        """ref/src/time_kernels.hpp:97-124 on every rank, with x_global[row] = f(row) on entry: p = 1*x + 0*x (+ the halo
+        exchange), max_iter x matvec(A, p, x), xdotp = sum over max_iter x dot(x, p) (rank-ordered global sums).
+        Returns ([x of every rank afterwards], xdotp)."""
+        xs, ps = [], []
+        for r in range(self.np):
+            nrows, first = self.nrows(r), int(self.csr(r)[0][0])
+            x = np.asarray(f(first + np.arange(nrows)), np.float64)
+            p = np.zeros(nrows + len(self.get_map("external_index", r)))
+            p[:nrows] = self.waxpby(1.0, x, 0.0, x)
+            p[self.get_map("external_local_index", r)] = f(self.get_map("external_index", r).astype(np.float64))
+            xs.append(x); ps.append(p)
+        for _ in range(max_iter):
+            xs = [self.matvec(ps[r], r, y0=xs[r]) for r in range(self.np)]
+        acc = 0.0
+        for _ in range(max_iter):
+            g = None
+            for r in range(self.np):
+                l = self.dot(xs[r], ps[r][:len(xs[r])])
+                g = l if g is None else g + l
+            acc = acc + g
+        return xs, acc
 
     @classmethod
     def waxpby(cls, alpha, x, beta, y):
@@ -307,8 +331,8 @@ class Ref:
         self.L.ref_bc_rows(self.h, which, _ptr(o))
         return o
 
-    def matvec(self, x, r=0):
-        y = np.zeros(self.nrows())
+    def matvec(self, x, r=0, y0=None):
+        y = np.zeros(self.nrows()) if y0 is None else np.array(y0, np.float64)
         self.L.ref_matvec(self.h, np.ascontiguousarray(x, np.float64), y)
         return y
 

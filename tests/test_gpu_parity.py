@@ -350,22 +350,6 @@ def test_verify_solution_on_device(n, whole, oracle_built, product_lib):
     assert mf.verify_solution(p.mesh, bad, 0.06, False if n[0] >= 10 else whole) == 1
 
 
-@pytest.mark.parametrize("n", [(20, 30, 40), (64, 64, 64)])
-def test_cg_history_bit_exact_with_programmatic_dependent_launch(n, oracle_built, product_lib):
-    """launch_cg with the programmatic-serialization attribute (kernels become resident while their predecessor drains and
-    block in griddepcontrol.wait): same bits, and the gated-off iterations after convergence still do nothing."""
-    o = Oracle(*n).setup()
-    want = o.cg_solve(200, EPS)
-    p = Problem(*n).setup()
-    p.mesh.set_option("pdl", 1)
-    for _ in range(2):
-        p.x.coefs[:] = 0.0
-        iters, normr, times, h = mf.cg_solve(p.A, p.b, p.x, mf.matvec_std(), 200, EPS, history=True)
-        assert iters == want["num_iters"]
-        assert_bits(h["normr"], want["normr"], "normr history (pdl)")
-        assert_bits(p.x.coefs, o.x(), "solution x (pdl)")
-
-
 def test_fused_reporting_mode_and_time_kernels(oracle_built, product_lib):
     """MINIFE_FUSED (ref/src/cg_solve.hpp:172-176): bit-identical history, the SpMV + p.Ap interval lands in cg_times[MATVECDOT];
     time_kernels (ref/src/time_kernels.hpp:97-124): p = x, x = A p, xdotp = sum of max_iter equal dots -- against the oracle."""
@@ -405,7 +389,7 @@ def test_two_pass_matvec_of_every_rank_bit_exact(n, npr, oracle_built, product_l
         x = rng.standard_normal(ncols)
         want = o.matvec(x, r)
         p.mesh.set_option("test_no_exchange", 1)
-        for overlap in (0, 1):
+        for overlap in (0, 1, 2):          # 1: the fused one-launch kernel (externals read through its halo pointer), 2: two launches
             p.mesh.set_option("overlap", overlap)
             for cfg in (0, 2, 4):
                 p.mesh.set_option("matvec_config", cfg)
@@ -442,12 +426,57 @@ def test_boxes_changed_by_add_imbalance(path, oracle_built, product_lib):
         assert_bits(p.b.coefs, o.b(r), "rank %d b" % r)
         x = rng.standard_normal(p.A.num_cols)
         p.mesh.set_option("test_no_exchange", 1)
-        for overlap in (0, 1):
+        for overlap in (0, 1, 2):
             p.mesh.set_option("overlap", overlap)
             y = np.zeros(p.A.num_rows())
             mf.matvec(p.A, x.copy(), y)
             assert_bits(y, o.matvec(x, r), "rank %d matvec overlap %d" % (r, overlap))
         p.mesh.close()
+
+
+def test_matvec_forms_beta_times_the_stale_y(oracle_built, product_lib):
+    """ref/src/SparseMatrix_functions.hpp:565-568: every row starts from beta*y[row] with beta = 0.  Value-neutral for a finite
+    positive y, but a negative or -0.0 stale y makes the seed -0.0 (which survives a row whose products are all -0.0) and a
+    non-finite one makes the row NaN.  Mesh matrix against the oracle, and a hand matrix against the literal loop."""
+    n = (6, 5, 4)
+    o = Oracle(*n).setup()
+    p = Problem(*n).setup()
+    nrows = p.A.num_rows()
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal(nrows)
+    x[rng.random(nrows) < 0.5] = -0.0                      # many rows with only zero products
+    y0 = rng.standard_normal(nrows)
+    y0[::7] = -0.0; y0[3::11] = np.nan; y0[5::13] = np.inf; y0[6::17] = -np.inf
+    for xx in (x, np.full(nrows, -0.0), np.zeros(nrows)):
+        want = o.matvec(xx, 0, y0=y0)
+        y = y0.copy()
+        mf.matvec(p.A, xx.copy(), y)
+        nan = np.isnan(want)
+        assert np.array_equal(np.isnan(y), nan)
+        assert_bits(y[~nan], want[~nan], "matvec with stale y")
+    p.mesh.close()
+    # all-positive coefficients times x = -0.0: every product is -0.0, so the sign of the result is the sign of 0*y[row]
+    nr = 40
+    lens = np.full(nr, 3); lens[[5, 6, 17]] = 0          # and rows without entries: the result IS 0*y[row]
+    ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    nz = int(ro[-1])
+    cols = ((np.arange(nz) * 7) % nr).astype(np.int32)
+    coefs = np.abs(rng.standard_normal(nz)) + 0.5
+    h = Problem(2, 2, 2).structure()
+    assert mf.lib().mfe_import_csr(h.mesh._h, nr, nr, ro, cols, coefs) == 0
+    xz = np.full(nr, -0.0)
+    y0 = np.where(np.arange(nr) % 3 == 0, -2.5, np.where(np.arange(nr) % 3 == 1, -0.0, 4.0))
+    want = np.empty(nr)
+    for r in range(nr):
+        s_ = np.float64(0.0) * np.float64(y0[r])
+        for i in range(ro[r], ro[r + 1]):
+            s_ = s_ + np.float64(coefs[i]) * np.float64(xz[cols[i]])
+        want[r] = s_
+    assert np.signbit(want).any() and not np.signbit(want).all()
+    y = y0.copy()
+    assert mf.lib().mfe_matvec(h.mesh._h, xz.copy(), y) == 0
+    assert_bits(y, want, "hand matrix, -0.0 products")
+    h.mesh.close()
 
 
 def test_pll_matvec_known_answers(product_lib):

@@ -4,12 +4,13 @@ import argparse, ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minife_b200 as mf
-ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=256); ap.add_argument("--iters", type=int, default=20)
+ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=256); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--fold", type=int, default=1); ap.add_argument("--warps", type=int, default=0)
 args = ap.parse_args()
 n = args.nx
 g = mf.Box([0, n, 0, n, 0, n]); mesh = mf.simple_mesh_description(g, g)
 A = mf.CSRMatrix(); mf.generate_matrix_structure(mesh, A); mf.assemble_FE_data(mesh, A, None)
 mf.impose_dirichlet(0.0, A, None, bc_rows=0); mf.impose_dirichlet(1.0, A, None, bc_rows=1); mf.make_local_matrix(A)
+mesh.set_option('dot_fold', args.fold); mesh.set_option('dot_maps_warps', args.warps)
 L = mf.lib(); st = np.zeros(16 + 1024, np.uint64)
 L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 1)
 it, nr, t = mf.cg_solve(A, None, None, None, args.iters, 2.2e-16)
@@ -22,4 +23,6 @@ for i in range(min(int(st[0]), 40)):
         print("  dot %3d: dirty %4d slow gaps %3d walk %.3f ms" % (i, w & 0xffffffff, w >> 32, st[17 + 2 * i] / 1e6))
     except BrokenPipeError:
         break
+for what in ("dot_rr", "dot_pap", "r_update", "xr_update", "waxpby", "matvec_dot"):
+    print("  time_kernel %-10s %.2f us" % (what, 1e3 * mesh.time_kernel(what, 20)))
 mesh.close()
