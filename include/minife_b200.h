@@ -62,6 +62,12 @@ int mfe_impose_dirichlet(mfe_ctx *ctx, double prescribed_value, int which_set);
 /* ref/src/make_local_matrix.hpp:42-442 */
 int mfe_make_local_matrix(mfe_ctx *ctx, int64_t *num_cols);
 
+/* ref/src/SparseMatrix_functions.hpp:319-408 rearrange_matrix_local_external, which the driver calls before cg_solve when
+ * mv_overlap_comm_comp=1 (driver.hpp:278-282): every row is re-sorted so that its owned columns come first and its external
+ * columns after them; the SpMV then sums each row exactly as the reference's matvec_overlap does (624-675: local entries
+ * onto 0*y, external entries onto 1*y), which changes the rounding of the rows that have externals and hence the history. */
+int mfe_rearrange_matrix_local_external(mfe_ctx *ctx);
+
 /* ref/src/cg_solve.hpp:69-229 with matvec_std (SparseMatrix_functions.hpp:546-578).
  * x_host: in = initial guess, out = solution (nrows doubles; NULL: use/keep the device-resident x).
  * normr_hist (NULL or max_iter+1 doubles): hist[0] = initial residual norm, hist[k] = the norm the reference

@@ -10,6 +10,7 @@ from ._lib import lib, LibraryError, library_path  # noqa: F401
 from .api import (  # noqa: F401
     Box, Parameters, simple_mesh_description, CSRMatrix, Vector, box_partition,
     generate_matrix_structure, assemble_FE_data, impose_dirichlet, make_local_matrix,
+    rearrange_matrix_local_external, matvec_overlap,
     cg_solve, matvec_std, matvec, waxpby, dot, exchange_externals, comm_unique_id, verify_solution, time_kernels,
     WAXPY, DOT, MATVEC, MATVECDOT, TOTAL, NUM_TIMERS, DOT_EXACT, DOT_SERIAL, DOT_TREE,
 )
@@ -17,5 +18,5 @@ from .api import (  # noqa: F401
 __all__ = [
     "lib", "LibraryError", "library_path", "Box", "Parameters", "simple_mesh_description", "CSRMatrix", "Vector",
     "box_partition", "generate_matrix_structure", "assemble_FE_data", "impose_dirichlet", "make_local_matrix",
-    "cg_solve", "matvec_std", "matvec", "waxpby", "dot", "exchange_externals", "comm_unique_id", "verify_solution", "time_kernels",
+    "rearrange_matrix_local_external", "matvec_overlap", "cg_solve", "matvec_std", "matvec", "waxpby", "dot", "exchange_externals", "comm_unique_id", "verify_solution", "time_kernels",
 ]

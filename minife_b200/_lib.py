@@ -35,6 +35,7 @@ SIGNATURES = {
     "mfe_assemble_FE_data": (C.c_int, [_vp]),
     "mfe_impose_dirichlet": (C.c_int, [_vp, C.c_double, C.c_int]),
     "mfe_make_local_matrix": (C.c_int, [_vp, _pi64]),
+    "mfe_rearrange_matrix_local_external": (C.c_int, [_vp]),
     "mfe_cg_solve": (C.c_int, [_vp, _vp, C.c_int, C.c_double, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp, _vp, _vp, _vp, _vp]),
     "mfe_time_kernels": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_double), _vp]),
     "mfe_verify_solution": (C.c_int, [_vp, C.c_double, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), _vp]),

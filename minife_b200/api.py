@@ -211,6 +211,19 @@ def make_local_matrix(A):
     A.has_local_indices = True
 
 
+def rearrange_matrix_local_external(A):
+    """ref/src/SparseMatrix_functions.hpp:319-408 (driver option mv_overlap_comm_comp=1, driver.hpp:278-282)."""
+    check(lib().mfe_rearrange_matrix_local_external(A._ctx()), "rearrange_matrix_local_external")
+
+
+class matvec_overlap:
+    """ref/src/SparseMatrix_functions.hpp:624-675: after rearrange_matrix_local_external the device SpMV sums every row in
+    this functor's order (local entries, then externals); the halo exchange is overlapped on the device either way."""
+
+    def __call__(self, A, x, y):
+        matvec_std()(A, x, y)
+
+
 class matvec_std:
     """ref/src/SparseMatrix_functions.hpp:546-578: ``matvec_std()(A, x, y)`` (x has num_cols entries)."""
 

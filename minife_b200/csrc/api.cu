@@ -118,6 +118,7 @@ struct mfe_ctx {
   cudaStream_t stream_x = nullptr;    // lower priority: the x update of iteration k runs here, beside the latency-bound dot kernels
   cudaEvent_t ev_alpha = nullptr, ev_xdone = nullptr;
   EventPool events;
+  int assembly_mode = 0;              // 0: element slab + row-owner gather kernels (default), 1: fused, element matrices in shared memory (measured slower)
   int x_overlap = 1;                  // 1: x += alpha*p on stream_x (off the critical path), 0: fused into the r update (one stream)
   int sm_count = 148;
   int64_t launches = 0;
@@ -153,7 +154,7 @@ struct mfe_ctx {
   int mv_cfg = 0;                // SpMV configuration (see matvec_configs): 16 warps x 1 stage, 2 gather batches per row
   int tr = MV_TILE_ROWS;         // rows per SpMV tile
   int dot_maps_warps = 0;        // warps per CTA of k_dot_maps: 0 = default (24), else 16 or 24
-  int dot_fold = 1;              // 1: the dot walk runs in the last CTA of k_dot_maps, 0: as its own one-CTA launch
+  int dot_maps_version = 0;      // 0: piece-level fast path (round 2), 1: the round-1 kernel (A/B measurements)
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -322,7 +323,7 @@ static void free_vectors(mfe_ctx *c)
   free_dev(c->dot.chunk_sums_a); free_dev(c->dot.piece_sums_a); free_dev(c->dot.chunk_sums_b); free_dev(c->dot.piece_sums_b);
   free_dev(c->dot.w.chunk_prefix); free_dev(c->dot.w.cta_maps); free_dev(c->dot.w.chunk_cnt);
   free_dev(c->dot.w.leaf_maps); free_dev(c->dot.w.warp_maps); free_dev(c->dot.w.super_maps); free_dev(c->dot.w.hyper_maps);
-  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.done_cnt); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.w.stats);
+  free_dev(c->dot.w.super_cnt); free_dev(c->dot.w.hyper_cnt); free_dev(c->dot.w.dirty_count); free_dev(c->dot.w.dirty_list); free_dev(c->dot.w.result); free_dev(c->dot.w.stats);
   c->d_b = c->d_x = c->d_r = c->d_p = c->d_Ap = c->d_tmp1 = c->d_tmp2 = nullptr;
   c->dot = DotWs();
   c->vec_cap = 0;
@@ -506,11 +507,10 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
       dev_alloc(&c->dot.w.cta_maps, nchunks + 1) || dev_alloc(&c->dot.w.leaf_maps, (nchunks + 1) * DOT_CTA_THREADS) ||
       dev_alloc(&c->dot.w.warp_maps, npieces + 8) || dev_alloc(&c->dot.w.super_maps, nchunks / 32 + 2) ||
       dev_alloc(&c->dot.w.hyper_maps, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.chunk_cnt, nchunks + 1) || dev_alloc(&c->dot.w.super_cnt, nchunks / 32 + 2) ||
-      dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.done_cnt, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) ||
+      dev_alloc(&c->dot.w.hyper_cnt, nchunks / 1024 + 2) || dev_alloc(&c->dot.w.dirty_count, 1) || dev_alloc(&c->dot.w.dirty_list, DOT_MAX_DIRTY) ||
       dev_alloc(&c->dot.w.result, 1) || dev_alloc(&c->dot.w.stats, DOT_STATS_WORDS)) return 1;
   CK(cudaMemsetAsync(c->dot.w.stats, 0, 8 * DOT_STATS_WORDS, c->stream));
   CK(cudaMemsetAsync(c->dot.w.dirty_count, 0, sizeof(int), c->stream));
-  CK(cudaMemsetAsync(c->dot.w.done_cnt, 0, sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->dot.w.chunk_cnt, 0, sizeof(int) * (nchunks + 1), c->stream));
   CK(cudaMemsetAsync(c->dot.w.super_cnt, 0, sizeof(int) * (nchunks / 32 + 2), c->stream));
   CK(cudaMemsetAsync(c->dot.w.hyper_cnt, 0, sizeof(int) * (nchunks / 1024 + 2), c->stream));
@@ -518,6 +518,18 @@ static int ensure_vectors(mfe_ctx *c, int64_t nrows, int64_t ncols)
   CK(cudaMemsetAsync(c->dot.piece_sums_b, 0, 8 * (npieces + 1), c->stream));
   c->dot.w.chunk_sums = c->dot.chunk_sums_a; c->dot.w.piece_sums = c->dot.piece_sums_a;
   c->vec_cap = need;
+  return 0;
+}
+
+// cudaFuncSetAttribute once per (kernel instantiation, device); one process may drive several GPUs from several threads
+static std::mutex g_attr_mutex;
+template <typename K>
+static int set_smem_attr_once(K kern, bool (&done)[64], int device, size_t smem)
+{
+  std::lock_guard<std::mutex> lk(g_attr_mutex);
+  if (done[device & 63]) return 0;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  done[device & 63] = true;
   return 0;
 }
 
@@ -575,11 +587,10 @@ extern "C" int mfe_generate_matrix_structure(mfe_ctx *c, int64_t *nrows, int64_t
   return 0;
 }
 
-extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
+// round-1 scheme: element matrices into an SoA scratch slab in global memory (k_elements), then the row-owner gather
+// (k_gather_rows); kept as assembly_mode 0 for comparison
+static int assemble_two_kernels(mfe_ctx *c)
 {
-  if (!c || !c->has_structure || !c->mesh_csr) return fail("mfe_assemble_FE_data: call mfe_generate_matrix_structure first");
-  if (c->has_local) return fail("mfe_assemble_FE_data: matrix already has local indices");
-  CK(cudaSetDevice(c->device));
   PhaseTimer tm(c->stream);
   const MeshDesc &m = c->m;
   // element box + ghost layer (assemble_FE_data.hpp:59-70)
@@ -592,8 +603,12 @@ extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
   int planes = (int)std::max<int64_t>(1, (int64_t)(2LL << 30) / (eplane * 44 * 8) - 1);
   planes = std::min(planes, m.lnz);
   ElemSlab sl; sl.ex0 = eb[0]; sl.ey0 = eb[2]; sl.nex = nex; sl.ney = ney; sl.stride = eplane * (planes + 1);
-  double *KF = nullptr;
-  if (dev_alloc(&KF, sl.stride * 44)) return 1;
+  double *KF = nullptr, *tab = nullptr;
+  const int nmax = std::max(m.nx, std::max(m.ny, m.nz));
+  if (dev_alloc(&KF, sl.stride * 44) || dev_alloc(&tab, (int64_t)3 * nmax * 24)) return 1;
+  double *tx = tab, *ty = tab + (size_t)nmax * 24, *tz = tab + (size_t)2 * nmax * 24;
+  k_jacobian_tables<<<grid_for(3 * 8 * nmax, 128), 128, 0, c->stream>>>(m, tx, ty, tz);
+  c->launches++;
   cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
   double t_el = 0, t_ga = 0;
   for (int iz0 = m.nb[4]; iz0 < m.nb[5]; iz0 += planes) {
@@ -602,7 +617,7 @@ extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
     sl.ez0 = ez0; sl.nez = ez1 - ez0;
     cudaEventRecord(e0, c->stream);
     const int64_t ne = eplane * sl.nez;
-    if (ne > 0) { k_elements<<<grid_for(ne, 128), 128, 0, c->stream>>>(m, sl, KF); c->launches++; }
+    if (ne > 0) { k_elements_tables<<<grid_for(ne, 128), 128, 0, c->stream>>>(m, sl, tx, ty, tz, KF); c->launches++; }
     cudaEventRecord(e1, c->stream);
     const int64_t nr = (int64_t)m.lnx * m.lny * (iz1 - iz0);
     k_gather_rows<<<grid_for(nr, 128), 128, 0, c->stream>>>(m, sl, KF, iz0, iz1, c->d_roff, c->d_tile_base, c->tr, c->d_coefs, c->d_b);
@@ -615,9 +630,48 @@ extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
   cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
   c->t_assembly = tm.stop();
   c->t_assembly_elem = t_el; c->t_assembly_gather = t_ga;
-  cudaFree(KF);
+  cudaFree(KF); cudaFree(tab);
   CK(cudaGetLastError());
   return 0;
+}
+
+// element matrices stay in shared memory: k_jacobian_tables + k_assemble_fused (kernels.cuh)
+static int assemble_fused(mfe_ctx *c)
+{
+  PhaseTimer tm(c->stream);
+  const MeshDesc &m = c->m;
+  const int nmax = std::max(m.nx, std::max(m.ny, m.nz));
+  double *tab = nullptr; unsigned int *d_next = nullptr;
+  if (dev_alloc(&tab, (int64_t)3 * nmax * 24) || dev_alloc(&d_next, 1)) return 1;
+  CK(cudaMemsetAsync(d_next, 0, sizeof(unsigned int), c->stream));
+  double *tx = tab, *ty = tab + (size_t)nmax * 24, *tz = tab + (size_t)2 * nmax * 24;
+  k_jacobian_tables<<<grid_for(3 * 8 * nmax, 128), 128, 0, c->stream>>>(m, tx, ty, tz);
+  static bool attr_set[64] = { false };
+  if (set_smem_attr_once(k_assemble_fused, attr_set, c->device, ASM_SMEM_BYTES)) return 1;
+  AsmUnits u;
+  u.ncx = (m.lnx + ASM_BX - 1) / ASM_BX; u.ncy = (m.lny + ASM_BY - 1) / ASM_BY;
+  // z segments: enough work units to balance the SMs (~6 per SM), each long enough to amortise its extra element plane
+  const int64_t cols = (int64_t)u.ncx * u.ncy;
+  int ncz = (int)std::max<int64_t>(1, ((int64_t)c->sm_count * 6 + cols - 1) / cols);
+  ncz = std::min(ncz, std::max(1, m.lnz / 16));
+  u.zlen = (m.lnz + ncz - 1) / ncz;
+  u.ncz = (m.lnz + u.zlen - 1) / u.zlen;
+  const int grid = (int)std::min<int64_t>(c->sm_count, cols * u.ncz);
+  k_assemble_fused<<<grid, ASM_THREADS, ASM_SMEM_BYTES, c->stream>>>(m, u, tx, ty, tz, c->d_roff, c->d_tile_base, c->tr, c->d_coefs, c->d_b, d_next);
+  c->launches += 2;
+  c->t_assembly = tm.stop();
+  c->t_assembly_elem = c->t_assembly; c->t_assembly_gather = 0;
+  cudaFree(tab); cudaFree(d_next);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int mfe_assemble_FE_data(mfe_ctx *c)
+{
+  if (!c || !c->has_structure || !c->mesh_csr) return fail("mfe_assemble_FE_data: call mfe_generate_matrix_structure first");
+  if (c->has_local) return fail("mfe_assemble_FE_data: matrix already has local indices");
+  CK(cudaSetDevice(c->device));
+  return c->assembly_mode == 0 ? assemble_two_kernels(c) : assemble_fused(c);
 }
 
 extern "C" int mfe_impose_dirichlet(mfe_ctx *c, double val, int which)
@@ -651,19 +705,17 @@ static int classify_tiles(mfe_ctx *c)
   c->d_tile_base_flagged = nullptr; c->d_tiles_boundary = nullptr; c->n_interior = c->n_boundary = 0;
   if (c->ntiles <= 0 || c->ntiles > 0x7fffffffLL) return 0;
   unsigned char *d_flag = nullptr;
-  if (dev_alloc(&d_flag, c->ntiles) || dev_alloc(&c->d_tile_base_flagged, c->ntiles + 2)) return 1;
+  int *d_count = nullptr;
+  // the list can hold every tile (its true length is only known on the device); 4 bytes per 32 rows
+  if (dev_alloc(&d_flag, c->ntiles) || dev_alloc(&c->d_tile_base_flagged, c->ntiles + 2) || dev_alloc(&c->d_tiles_boundary, c->ntiles + 1) || dev_alloc(&d_count, 1)) return 1;
   k_classify_tiles<<<grid_for((c->ntiles + 1) * 32, 256), 256, 0, c->stream>>>(c->d_cols, c->d_tile_base, c->ntiles, (int)c->nrows, d_flag, c->d_tile_base_flagged);
-  c->launches++;
-  std::vector<unsigned char> flag(c->ntiles);
-  CK(cudaMemcpyAsync(flag.data(), d_flag, c->ntiles, cudaMemcpyDeviceToHost, c->stream));
+  k_compact_tiles<<<1, 1024, 0, c->stream>>>(d_flag, c->ntiles, c->d_tiles_boundary, d_count);
+  c->launches += 2;
+  int nb = 0;
+  CK(cudaMemcpyAsync(&nb, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  cudaFree(d_flag);
-  std::vector<int> bd;
-  for (int64_t t = 0; t < c->ntiles; ++t) if (flag[t]) bd.push_back((int)t);
-  c->n_boundary = (int64_t)bd.size(); c->n_interior = c->ntiles - c->n_boundary;
-  if (dev_alloc(&c->d_tiles_boundary, c->n_boundary + 1)) return 1;
-  if (!bd.empty()) CK(cudaMemcpyAsync(c->d_tiles_boundary, bd.data(), sizeof(int) * bd.size(), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_flag); cudaFree(d_count);
+  c->n_boundary = nb; c->n_interior = c->ntiles - nb;
   return 0;
 }
 
@@ -722,6 +774,18 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   return 0;
 }
 
+// ref/src/SparseMatrix_functions.hpp:319-408 (driver.hpp:278-282, mv_overlap_comm_comp=1)
+extern "C" int mfe_rearrange_matrix_local_external(mfe_ctx *c)
+{
+  if (!c || !c->has_structure || !c->has_local) return fail("mfe_rearrange_matrix_local_external: matrix needs local indices (mfe_make_local_matrix)");
+  CK(cudaSetDevice(c->device));
+  k_sort_rows_local<<<grid_for(c->nrows, 128), 128, 0, c->stream>>>(c->d_cols, c->d_coefs, c->d_roff, c->d_tile_base, c->tr, c->nrows);
+  c->launches++;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // kernels launchers
 // ---------------------------------------------------------------------------------------------------------
@@ -729,18 +793,6 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
 struct MvCfg { int g, s, h; };
 static const MvCfg matvec_configs[] = { {16, 1, 2}, {16, 1, 1}, {10, 2, 1}, {20, 1, 2}, {21, 1, 3} };
 enum { N_MV_CFG = sizeof(matvec_configs) / sizeof(matvec_configs[0]) };
-
-// cudaFuncSetAttribute once per (kernel instantiation, device); one process may drive several GPUs from several threads
-static std::mutex g_attr_mutex;
-template <typename K>
-static int set_smem_attr_once(K kern, bool (&done)[64], int device, size_t smem)
-{
-  std::lock_guard<std::mutex> lk(g_attr_mutex);
-  if (done[device & 63]) return 0;
-  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  done[device & 63] = true;
-  return 0;
-}
 
 template <int G, int S, int H, int MODE>
 static int launch_matvec_mode(mfe_ctx *c, const MvArgs &a)
@@ -906,12 +958,14 @@ static void launch_waxpby(mfe_ctx *c, int64_t n, ScalarArg a, const double *x, S
 }
 
 template <bool SAME, int NW>
-static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k, bool fold, const WalkArgs &wa)
+static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
 {
   static bool attr_set[64] = { false };
   const size_t smem = DotMapsCfg<SAME, NW>::SMEM_BYTES;
   auto kern = k_dot_maps<SAME, NW>;
   if (set_smem_attr_once(kern, attr_set, c->device, smem)) return 1;
+  static bool attr_set_v1[64] = { false };
+  if (c->dot_maps_version == 1 && set_smem_attr_once(k_dot_maps_v1<SAME, NW>, attr_set_v1, c->device, smem)) return 1;
   const int64_t npieces = (n + DOT_PIECE - 1) / DOT_PIECE;
   if (npieces == 0) return 0;
   // one persistent CTA per SM owning a contiguous range of pieces (more CTAs only when a range would overflow the table)
@@ -919,16 +973,17 @@ static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const dou
   grid = std::max<int64_t>(grid, (npieces + DOT_MAPS_MAX_PP - 1) / DOT_MAPS_MAX_PP);
   const int PP = (int)((npieces + grid - 1) / grid);
   grid = (npieces + PP - 1) / PP;
-  CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k, fold ? 1 : 0, wa));
+  if (c->dot_maps_version == 1) CK(launch_cg(c, k_dot_maps_v1<SAME, NW>, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
+  else CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
   return 0;
 }
 
-static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k, bool fold, const WalkArgs &wa)
+static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
 {
   if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail("dot: operands must be 16-byte aligned");
   const int nw = c->dot_maps_warps ? c->dot_maps_warps : 24;
-  if (x == y) return nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k, fold, wa) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k, fold, wa);
-  return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k, fold, wa) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k, fold, wa);
+  if (x == y) return nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k);
+  return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k);
 }
 
 // local dot of x,y (n terms) + rank-ordered global sum + CG scalar epilogue.
@@ -964,9 +1019,8 @@ static int launch_dot(mfe_ctx *c, int64_t n, const double *x, const double *y, i
     } else {
       WalkArgs wa{};
       wa.sc = sc; wa.epi = peer ? epi : epi_local; wa.k = k; wa.normr_hist = nh; wa.rtrans_hist = rh; wa.pap_hist = ph; wa.alpha_hist = ah; wa.pd = pd;
-      const bool fold = c->dot_fold != 0 && n > 0;      // the walk runs in the last CTA of the maps kernel
-      if (launch_dot_maps(c, n, x, y, w, gate, k, fold, wa)) return 1;
-      if (!fold) CK(launch_cg(c, k_dot_walk, dim3(1), dim3(WALK_THREADS), 0, n, x, y, w, gate, wa));
+      if (launch_dot_maps(c, n, x, y, w, gate, k)) return 1;
+      CK(launch_cg(c, k_dot_walk, dim3(1), dim3(WALK_THREADS), 0, n, x, y, w, gate, wa));
       finished = peer;
     }
   }
@@ -1321,7 +1375,8 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   }
   if (!strcmp(name, "fused")) { c->fused = value != 0; return 0; }
   if (!strcmp(name, "x_overlap")) { c->x_overlap = value != 0; return 0; }
-  if (!strcmp(name, "dot_fold")) { c->dot_fold = value != 0; return 0; }
+  if (!strcmp(name, "assembly_mode")) { c->assembly_mode = value != 0; return 0; }
+  if (!strcmp(name, "dot_maps_version")) { c->dot_maps_version = value != 0; return 0; }
   if (!strcmp(name, "test_no_exchange")) { c->test_no_exchange = value != 0; return 0; }
   if (!strcmp(name, "ell_width")) {          // ref/src/ELLMatrix.hpp: 0 = CSR semantics, 27 = the width generate_matrix_structure reserves
     if (value < 0 || value > 64) return fail("mfe_set_option: ell_width must be in [0,64]");

@@ -47,6 +47,38 @@ MFE_HD void gather_row(const MeshDesc &m, const ElemSlab &sl, const double *KF, 
       }
 }
 
+// The same gather out of a two-plane ring of element matrices in shared memory (k_assemble_fused): element plane ez lives in
+// slot ez & 1; inside a plane the elements of the CTA's window are numbered e2 = (ex - wx0) + wnx * (ey - wy0);
+// KF[(slot * 44 + k) * wstride + e2].
+MFE_HD void gather_row_ring(const MeshDesc &m, const double *KF, int wx0, int wy0, int wnx, int wstride, int ix, int iy, int iz, double *acc, double &bsum)
+{
+#pragma unroll
+  for (int s = 0; s < 27; ++s) acc[s] = 0.0;
+  bsum = 0.0;
+#pragma unroll
+  for (int dz = -1; dz <= 0; ++dz)
+#pragma unroll
+    for (int dy = -1; dy <= 0; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 0; ++dx) {
+        const int ex = ix + dx, ey = iy + dy, ez = iz + dz;
+        if (ex < 0 || ey < 0 || ez < 0 || ex >= m.nx || ey >= m.ny || ez >= m.nz) continue;
+        const double *E = KF + (size_t)((ez & 1) * 44) * wstride + ((ex - wx0) + wnx * (ey - wy0));
+        const int li = hex8_local_node(-dx, -dy, -dz);     // position of the row node inside this element
+#pragma unroll
+        for (int qz = 0; qz <= 1; ++qz)
+#pragma unroll
+          for (int qy = 0; qy <= 1; ++qy)
+#pragma unroll
+            for (int qx = 0; qx <= 1; ++qx) {
+              const int lj = hex8_local_node(qx, qy, qz);
+              const int s = (dz + qz + 1) * 9 + (dy + qy + 1) * 3 + (dx + qx + 1);
+              acc[s] = MFE_ADD(acc[s], E[(size_t)hex8_sym_index(li, lj) * wstride]);
+            }
+        bsum = MFE_ADD(bsum, E[(size_t)(36 + li) * wstride]);
+      }
+}
+
 // write the row's values at their sorted-column positions
 MFE_HD void store_row(const MeshDesc &m, int ix, int iy, int iz, int64_t off, const double *acc, double *coefs)
 {

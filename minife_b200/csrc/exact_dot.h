@@ -472,7 +472,6 @@ struct DotWork {
   int *super_cnt;          //                                    chunks of a super
   int *hyper_cnt;          //                                    supers of a hyper
   int *dirty_count;        // 1
-  int *done_cnt;           // 1: CTAs of k_dot_maps that finished (self-resetting); the last one runs the walk
   int *dirty_list;         // DOT_MAX_DIRTY leaf indices
   double *result;          // 1
   unsigned long long *stats; // optional diagnostics (DOT_STATS_WORDS words): see k_dot_walk

@@ -21,12 +21,13 @@ struct LocalMaps {
   int64_t num_cols = 0;
 };
 
-// externals of rank p (nodes of the one-node shell around p's node box, owned by someone else), in the
-// reference's first-encounter order.  `gm.boxes` must be a HOST table.
-inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
+// Visit the externals of rank p (nodes of the one-node shell around p's node box, owned by someone else) in no particular
+// order.  `gm.boxes` must be a HOST table.  fn(first, grow, owner): first = the smallest adjacent owned local row (the row in
+// which the reference's scan meets the external first), grow = its global row, owner = its rank.
+template <typename F>
+inline void for_each_external(const MeshDesc &gm, int p, F fn)
 {
   const RankBox &B = gm.boxes[p];
-  out.clear();
   if (B.nrows == 0) return;
   MeshDesc m = gm;
   m.rank = p;
@@ -36,13 +37,11 @@ inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
   const int lo[3] = { std::max(B.nb[0] - 1, 0), std::max(B.nb[2] - 1, 0), std::max(B.nb[4] - 1, 0) };
   const int hi[3] = { std::min(B.nb[1] + 1, gm.gnx), std::min(B.nb[3] + 1, gm.gny), std::min(B.nb[5] + 1, gm.gnz) };
   auto add = [&](int x, int y, int z) {
-    ExtEntry e;
     const int fx = std::max(B.nb[0], x - 1), fy = std::max(B.nb[2], y - 1), fz = std::max(B.nb[4], z - 1);
-    e.first = (int64_t)(fx - B.nb[0]) + (int64_t)m.lnx * ((fy - B.nb[2]) + (int64_t)m.lny * (fz - B.nb[4]));
+    const int64_t first = (int64_t)(fx - B.nb[0]) + (int64_t)m.lnx * ((fy - B.nb[2]) + (int64_t)m.lny * (fz - B.nb[4]));
     int ox, oy, oz;
-    e.grow = node_to_row(m, x, y, z);
-    e.owner = row_to_node(m, e.grow, ox, oy, oz);
-    out.push_back(e);
+    const int grow = node_to_row(m, x, y, z);
+    fn(first, grow, row_to_node(m, grow, ox, oy, oz));
   };
   for (int z = lo[2]; z < hi[2]; ++z)
     for (int y = lo[1]; y < hi[1]; ++y) {
@@ -53,7 +52,38 @@ inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
         if (hi[0] > B.nb[1]) add(B.nb[1], y, z);
       }
     }
-  std::sort(out.begin(), out.end(), [](const ExtEntry &a, const ExtEntry &b) { return a.first != b.first ? a.first < b.first : a.grow < b.grow; });
+}
+
+inline bool ext_before(const ExtEntry &a, const ExtEntry &b) { return a.first != b.first ? a.first < b.first : a.grow < b.grow; }
+
+// externals of rank p in the reference's first-encounter order
+inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
+{
+  out.clear();
+  for_each_external(gm, p, [&](int64_t first, int grow, int owner) { out.push_back(ExtEntry{ first, grow, owner }); });
+  std::sort(out.begin(), out.end(), ext_before);
+}
+
+// What rank p receives from rank `me`, without sorting p's whole shell: its externals owned by `me` in p's encounter order
+// (-> my elements_to_send for p) and the offset of that group inside p's external tail.  p groups its externals by owner
+// in the order in which it first meets each owner (make_local_matrix.hpp:153-166), so the offset is the number of
+// externals whose owner is first met before `me` is: one linear pass over the shell for the per-owner counts and
+// first-encounter keys, one sort of my (small) group.
+inline void peer_wants_from(const MeshDesc &gm, int p, int me, std::vector<ExtEntry> &mine, int &dst_offset)
+{
+  mine.clear();
+  std::vector<int> cnt(gm.nranks, 0);
+  std::vector<ExtEntry> firstkey(gm.nranks, ExtEntry{ 0, 0, -1 });
+  for_each_external(gm, p, [&](int64_t first, int grow, int owner) {
+    const ExtEntry e{ first, grow, owner };
+    if (cnt[owner]++ == 0 || ext_before(e, firstkey[owner])) firstkey[owner] = e;
+    if (owner == me) mine.push_back(e);
+  });
+  std::sort(mine.begin(), mine.end(), ext_before);
+  dst_offset = 0;
+  if (cnt[me] == 0) return;
+  for (int q = 0; q < gm.nranks; ++q)
+    if (q != me && cnt[q] > 0 && ext_before(firstkey[q], firstkey[me])) dst_offset += cnt[q];
 }
 
 // group by owner in first-encounter order of owners, encounter order inside a group (make_local_matrix.hpp:153-166)
@@ -90,16 +120,13 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
   // what each neighbour needs from me, in ITS external order (make_local_matrix.hpp:386-429)
   L.send_length.assign(L.neighbors.size(), 0);
   L.send_dst_offset.assign(L.neighbors.size(), 0);
-  std::vector<ExtEntry> pext; std::vector<int> pown; std::vector<std::vector<int>> pgrp;
+  std::vector<ExtEntry> mine;
   for (size_t i = 0; i < L.neighbors.size(); ++i) {
-    externals_of(gm, L.neighbors[i], pext);
-    group_externals(pext, pown, pgrp);
     int poff = 0;
-    for (size_t g = 0; g < pown.size(); poff += (int)pgrp[g].size(), ++g) if (pown[g] == rank) {
-      L.send_length[i] = (int)pgrp[g].size();
-      L.send_dst_offset[i] = poff;
-      for (int e : pgrp[g]) L.elements_to_send.push_back(pext[e].grow - first_row);
-    }
+    peer_wants_from(gm, L.neighbors[i], rank, mine, poff);
+    L.send_length[i] = (int)mine.size();
+    L.send_dst_offset[i] = poff;
+    for (const ExtEntry &e : mine) L.elements_to_send.push_back(e.grow - first_row);
   }
   L.num_cols = (int64_t)nrows + n_ext;
 }

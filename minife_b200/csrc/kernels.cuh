@@ -114,6 +114,21 @@ __global__ void k_tile_base_csr(const uint32_t *__restrict__ roff, int64_t nrows
 __constant__ double c_grad[192];
 __constant__ double c_psi[64];
 
+// tab[axis]: per element index along the axis, 8 Gauss points x 3 entries of the Jacobian column (hex8_jacobian_column)
+__global__ void k_jacobian_tables(MeshDesc m, double *__restrict__ tx, double *__restrict__ ty, double *__restrict__ tz)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nmax = max(m.nx, max(m.ny, m.nz));
+  if (t >= 3 * 8 * nmax) return;
+  const int axis = t / (8 * nmax), e = (t / 8) % nmax, g = t % 8;
+  const int n = axis == 0 ? m.nx : axis == 1 ? m.ny : m.nz;
+  if (e >= n) return;
+  // get_coords (ref/utils/box_utils.hpp:68-82): 1.0*i/n, one division; h = 1.0/n; high face = low + h
+  const double c0 = __ddiv_rn((double)e, (double)n), h = __ddiv_rn(1.0, (double)n), c1 = __dadd_rn(c0, h);
+  double *out = (axis == 0 ? tx : axis == 1 ? ty : tz) + ((size_t)e * 8 + g) * 3;
+  hex8_jacobian_column(c_grad, g, axis, c0, c1, out);
+}
+
 __global__ void __launch_bounds__(128) k_elements(MeshDesc m, ElemSlab sl, double *__restrict__ KF)
 {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -127,6 +142,25 @@ __global__ void __launch_bounds__(128) k_elements(MeshDesc m, ElemSlab sl, doubl
   const double hx = __ddiv_rn(1.0, (double)m.nx), hy = __ddiv_rn(1.0, (double)m.ny), hz = __ddiv_rn(1.0, (double)m.nz);
   double K[36], f[8];
   hex8_element(c_grad, c_psi, x, y, z, hx, hy, hz, K, f);
+#pragma unroll
+  for (int k = 0; k < 36; ++k) KF[(int64_t)k * sl.stride + e] = K[k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) KF[(int64_t)(36 + k) * sl.stride + e] = f[k];
+}
+
+// The same with the Jacobian columns taken from the per-axis tables (k_jacobian_tables, hex8_jacobian_column): 1152 of the
+// ~4800 multiply-adds per element disappear, bit-identical results (the kernel is FP64-pipe bound).
+__global__ void __launch_bounds__(128) k_elements_tables(MeshDesc m, ElemSlab sl, const double *__restrict__ tx, const double *__restrict__ ty,
+                                                         const double *__restrict__ tz, double *__restrict__ KF)
+{
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t ne = (int64_t)sl.nex * sl.ney * sl.nez;
+  if (e >= ne) return;
+  const int ex = sl.ex0 + (int)(e % sl.nex);
+  const int ey = sl.ey0 + (int)((e / sl.nex) % sl.ney);
+  const int ez = sl.ez0 + (int)(e / ((int64_t)sl.nex * sl.ney));
+  double K[36], f[8];
+  hex8_element_tables(c_grad, c_psi, tx + (size_t)ex * 24, ty + (size_t)ey * 24, tz + (size_t)ez * 24, K, f);
 #pragma unroll
   for (int k = 0; k < 36; ++k) KF[(int64_t)k * sl.stride + e] = K[k];
 #pragma unroll
@@ -158,6 +192,74 @@ __global__ void __launch_bounds__(128) k_gather_rows(MeshDesc m, ElemSlab sl, co
   const int64_t off = tile_base[t] + (int64_t)(uint32_t)(roff[lr] - roff[t * tr]);
   b[lr] = bsum;
   store_row(m, ix, iy, iz, off, acc, coefs);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fused assembly: element matrices never leave the SM.  A work unit is a column of ASM_BX x ASM_BY owned nodes over a range
+// of node planes; the CTA marches through the planes with a two-plane ring of element matrices in shared memory:
+//   compute element plane iz (one element per thread, per-axis Jacobian tables: hex8_jacobian_column) -> barrier ->
+//   every row of node plane iz gathers its <= 8 elements from planes iz-1 and iz in ascending element id (the order of the
+//   reference's scatter, SparseMatrix_functions.hpp:183-255) and writes its 27 coefficients and b -> barrier.
+// The window of elements is one wider than the node column in x and y, so elements on the seams between columns are
+// computed twice (16*17 elements for 15*16 rows: +13 %); nothing is written to global memory but A and b.
+// The element computation is FP64-pipe bound (~3.7 k mul/add per element, no FMA: one rounding per reference operation).
+// ------------------------------------------------------------------------------------------------------
+enum { ASM_BX = 15, ASM_BY = 16, ASM_WX = ASM_BX + 1, ASM_WY = ASM_BY + 1, ASM_NE = ASM_WX * ASM_WY, ASM_THREADS = 288 };
+static_assert(ASM_NE <= ASM_THREADS && ASM_BX * ASM_BY <= ASM_THREADS, "one element and one row per thread");
+#define ASM_SMEM_BYTES (2 * 44 * ASM_NE * 8)
+
+struct AsmUnits { int ncx, ncy, ncz, zlen; };     // columns in x / y, z segments, node planes per segment
+
+__global__ void __launch_bounds__(ASM_THREADS, 1)
+k_assemble_fused(MeshDesc m, AsmUnits u, const double *__restrict__ tx, const double *__restrict__ ty, const double *__restrict__ tz,
+                 const uint32_t *__restrict__ roff, const int64_t *__restrict__ tile_base, int tr, double *__restrict__ coefs,
+                 double *__restrict__ b, unsigned int *__restrict__ next_unit)
+{
+  extern __shared__ __align__(16) double KF[];          // [2][44][ASM_NE]
+  __shared__ int unit_s;
+  const int tid = threadIdx.x;
+  const int nunits = u.ncx * u.ncy * u.ncz;
+  for (;;) {
+    __syncthreads();                                     // everybody is done with the previous unit (ring and unit_s)
+    if (tid == 0) unit_s = (int)atomicAdd(next_unit, 1u);
+    __syncthreads();
+    const int unit = unit_s;
+    if (unit >= nunits) return;
+    const int cx = unit % u.ncx, cy = (unit / u.ncx) % u.ncy, cz = unit / (u.ncx * u.ncy);
+    const int bx0 = m.nb[0] + cx * ASM_BX, by0 = m.nb[2] + cy * ASM_BY;
+    const int z0 = m.nb[4] + cz * u.zlen, z1 = min(z0 + u.zlen, m.nb[5]);
+    const int wx0 = bx0 - 1, wy0 = by0 - 1;              // element window (may start at -1: such elements do not exist)
+    // my element of every plane, my row of every plane
+    const int ex = wx0 + tid % ASM_WX, ey = wy0 + tid / ASM_WX;
+    const bool elem_ok = tid < ASM_NE && ex >= 0 && ey >= 0 && ex < m.nx && ey < m.ny && ex < m.nb[1] && ey < m.nb[3];
+    const int ix = bx0 + tid % ASM_BX, iy = by0 + tid / ASM_BX;
+    const bool row_ok = tid < ASM_BX * ASM_BY && ix < m.nb[1] && iy < m.nb[3];
+    auto element_plane = [&](int ez) {
+      if (!elem_ok || ez < 0 || ez >= m.nz) return;
+      double K[36], f[8];
+      hex8_element_tables(c_grad, c_psi, tx + (size_t)ex * 24, ty + (size_t)ey * 24, tz + (size_t)ez * 24, K, f);
+      double *E = KF + (size_t)((ez & 1) * 44) * ASM_NE + tid;
+#pragma unroll
+      for (int k = 0; k < 36; ++k) E[k * ASM_NE] = K[k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) E[(36 + k) * ASM_NE] = f[k];
+    };
+    element_plane(z0 - 1);
+    for (int iz = z0; iz < z1; ++iz) {
+      element_plane(iz);
+      __syncthreads();
+      if (row_ok) {
+        double acc[27], bsum;
+        gather_row_ring(m, KF, wx0, wy0, ASM_WX, ASM_NE, ix, iy, iz, acc, bsum);
+        const int64_t lr = (int64_t)(ix - m.nb[0]) + (int64_t)m.lnx * ((iy - m.nb[2]) + (int64_t)m.lny * (iz - m.nb[4]));
+        const int64_t t = lr / tr;
+        const int64_t off = tile_base[t] + (int64_t)(uint32_t)(roff[lr] - roff[t * tr]);
+        b[lr] = bsum;
+        store_row(m, ix, iy, iz, off, acc, coefs);
+      }
+      __syncthreads();                                   // plane iz-1 may be overwritten by plane iz+1
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -194,6 +296,29 @@ __global__ void k_localize_cols(int *__restrict__ cols, int64_t nnz, int start_r
     int lo = 0, hi = n_ext;
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (ext_sorted_global[mid] < c) lo = mid + 1; else hi = mid; }
     cols[i] = (lo < n_ext && ext_sorted_global[lo] == c) ? ext_sorted_local[lo] : -1;
+  }
+}
+
+// rearrange_matrix_local_external: ref/src/SparseMatrix_functions.hpp:319-408.  The reference sorts every row by local column
+// index (owned columns first, externals after them) and matvec_overlap (624-675) then sums the local entries onto 0*y and
+// the external ones onto 1*y -- per row ONE left-to-right pass over the re-sorted row, since 1*y is exact.  So re-sorting
+// the rows in place is all it takes for k_matvec to return matvec_overlap's bits (only rows with externals change).
+__global__ void k_sort_rows_local(int *__restrict__ cols, double *__restrict__ coefs, const uint32_t *__restrict__ roff,
+                                  const int64_t *__restrict__ tile_base, int tr, int64_t nrows)
+{
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  const int64_t t = r / tr;
+  const int64_t off = tile_base[t] + (int64_t)(uint32_t)(roff[r] - roff[t * tr]);
+  const int len = (int)(uint32_t)(roff[r + 1] - roff[r]);
+  bool sorted = true;
+  for (int i = 1; i < len; ++i) sorted = sorted && cols[off + i - 1] <= cols[off + i];
+  if (sorted) return;
+  for (int i = 1; i < len; ++i) {            // insertion sort of (cols, coefs) by column
+    const int c = cols[off + i]; const double v = coefs[off + i];
+    int j = i;
+    for (; j > 0 && cols[off + j - 1] > c; --j) { cols[off + j] = cols[off + j - 1]; coefs[off + j] = coefs[off + j - 1]; }
+    cols[off + j] = c; coefs[off + j] = v;
   }
 }
 

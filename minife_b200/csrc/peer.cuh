@@ -194,4 +194,30 @@ __global__ void k_classify_tiles(const int *__restrict__ cols, const int64_t *__
   if (lane == 0) { is_boundary[t] = any != 0; tile_base_flagged[t] = tile_base[t] | (any ? (1LL << 62) : 0LL); }
 }
 
+// ascending list of the flagged tiles (one CTA; ntiles is ~0.5 M at 256^3 per rank): every thread counts the flags of its
+// contiguous run of tiles, a block-wide exclusive scan places the runs, every thread writes its indices
+__global__ void __launch_bounds__(1024) k_compact_tiles(const unsigned char *__restrict__ is_boundary, int64_t ntiles, int *__restrict__ list, int *__restrict__ count)
+{
+  __shared__ int wtot[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t run = (ntiles + blockDim.x - 1) / blockDim.x, t0 = (int64_t)tid * run, t1 = t0 + run < ntiles ? t0 + run : ntiles;
+  int mine = 0;
+  for (int64_t t = t0; t < t1; ++t) mine += is_boundary[t] != 0;
+  int inc = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+  if (lane == 31) wtot[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int v = wtot[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += u; }
+    wtot[lane] = iv - v;
+    if (lane == 31) *count = iv;
+  }
+  __syncthreads();
+  int pos = wtot[warp] + inc - mine;
+  for (int64_t t = t0; t < t1; ++t) if (is_boundary[t]) list[pos++] = (int)t;
+}
+
 }  // namespace mfe

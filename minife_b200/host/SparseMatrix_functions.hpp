@@ -64,9 +64,14 @@ parallel_memory_overhead_MB(const MatrixType& A)
   return mem_MB;
 }
 
-// ref/src/SparseMatrix_functions.hpp:319-408: the interior/boundary split is private to the device SpMV
+// ref/src/SparseMatrix_functions.hpp:319-408: on the device every row is re-sorted in place (owned columns first, externals
+// after them), which makes the SpMV sum the rows in matvec_overlap's order (mfe_rearrange_matrix_local_external); the host
+// struct keeps the arrays the driver has already reported and dumped.
 template<typename MatrixType>
-void rearrange_matrix_local_external(MatrixType& /*A*/) {}
+void rearrange_matrix_local_external(MatrixType& A)
+{
+  if (mfe_rearrange_matrix_local_external(b200::entry_of(&A, "rearrange_matrix_local_external").ctx) != 0) b200::die("rearrange_matrix_local_external");
+}
 
 // ref/src/SparseMatrix_functions.hpp:431-480.  `bc_rows` must be one of the two sets of the mesh the matrix was
 // generated from (that is what driver.hpp:215-218 passes); on the device the sets are closed-form.

@@ -537,6 +537,28 @@ void mfo_matvec(mfo_world *w, int rank, const double *x, double *y)
     y[row] = sum;
   }
 }
+/* ---- ref/src/SparseMatrix_functions.hpp:319-408 rearrange_matrix_local_external + 624-675 matvec_overlap -------
+ * The reference sorts every row by (local) column index (sort_with_companions, 347), which puts the owned columns
+ * (< nrows) first and the externals after them, then moves the external entries of all rows to the back of the packed
+ * arrays (row_offsets_external).  matvec_overlap sums a row's local entries onto 0*y (first loop, 649-657), stores, and
+ * adds its external entries onto 1*y (second loop, 664-672): per row that is ONE left-to-right pass over
+ * [locals ascending | externals ascending], because 1*y is exact.  So the oracle keeps one CSR and only re-sorts each
+ * row; mfo_matvec then returns matvec_overlap's bits. */
+void mfo_rearrange_matrix_local_external(mfo_world *w)
+{
+  int p;
+  for (p = 0; p < w->np; ++p) {
+    mfo_rank *R = &w->r[p]; int row;
+    for (row = 0; row < R->nrows; ++row) {
+      int b = R->row_offsets[row], e = R->row_offsets[row + 1], i, j;
+      for (i = b + 1; i < e; ++i) {           /* insertion sort of (cols, coefs) by column */
+        int c = R->cols[i]; double v = R->coefs[i];
+        for (j = i; j > b && R->cols[j - 1] > c; --j) { R->cols[j] = R->cols[j - 1]; R->coefs[j] = R->coefs[j - 1]; }
+        R->cols[j] = c; R->coefs[j] = v;
+      }
+    }
+  }
+}
 /* ---- ref/src/Vector_functions.hpp:127-150, 194-226 --------------------------------------------- */
 void mfo_waxpby(long long n, double alpha, const double *x, double beta, const double *y, double *wv)
 {

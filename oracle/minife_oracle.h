@@ -75,6 +75,10 @@ void mfo_exchange_externals(mfo_world *w, double **x_per_rank);
 void mfo_waxpby(long long n, double alpha, const double *x, double beta, const double *y, double *w); /* Vector_functions.hpp:127-150 */
 double mfo_dot(long long n, const double *x, const double *y);                                       /* Vector_functions.hpp:194-226 */
 
+/* ref/src/SparseMatrix_functions.hpp:319-408 (+ 624-675): after this, mfo_matvec / mfo_cg_solve sum every row in the order
+ * of the reference's matvec_overlap (local entries first, then externals; driver option mv_overlap_comm_comp=1) */
+void mfo_rearrange_matrix_local_external(mfo_world *w);
+
 #ifdef __cplusplus
 }
 #endif

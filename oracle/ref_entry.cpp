@@ -279,6 +279,20 @@ int ref_cg_solve(void* h, int max_iter, double tol, int* num_iters, double* norm
 // that every per-iteration scalar is observable.  tests/ check that it ends bit-identical
 // to ref_cg_solve.  Sequence follows ref/src/cg_solve.hpp:124-215.
 // normr_hist[k] (k=0..num_iters): residual norm as the reference would report for iteration k.
+static int g_trace_overlap = 0;   // 1: the trace uses the reference's matvec_overlap (after rearrange_matrix_local_external)
+struct TraceMatvec {
+  void operator()(RefMatrix& A, RefVector& x, RefVector& y) {
+    if (g_trace_overlap) { miniFE::matvec_overlap<RefMatrix, RefVector> mv; mv(A, x, y); }
+    else { miniFE::matvec_std<RefMatrix, RefVector> mv; mv(A, x, y); }
+  }
+};
+void ref_rearrange_matrix_local_external(void* h)
+{
+  RefProblem* P = static_cast<RefProblem*>(h);
+  miniFE::rearrange_matrix_local_external(P->A);
+  g_trace_overlap = 1;
+}
+
 int ref_cg_trace(void* h, int max_iter, double tol, int* num_iters, double* normr_out,
                  double* normr_hist, double* rtrans_hist, double* pap_hist, double* alpha_hist)
 {
@@ -288,7 +302,7 @@ int ref_cg_trace(void* h, int max_iter, double tol, int* num_iters, double* norm
   RefVector& x = *P->x;
   size_t nrows = A.rows.size();
   RefVector r(b.startIndex, nrows), p(0, A.num_cols), Ap(b.startIndex, nrows);
-  miniFE::matvec_std<RefMatrix, RefVector> mv;
+  TraceMatvec mv;
   double one = 1.0, zero = 0.0;
   miniFE::waxpby(one, x, zero, x, p);
   mv(A, p, Ap);
@@ -462,6 +476,8 @@ int main(int argc, char** argv)
   dumpv(dir, "recv_length", numprocs, myproc, "i32", P->A.recv_length);
   dumpv(dir, "send_length", numprocs, myproc, "i32", P->A.send_length);
 #endif
+  // REF_DUMP_OVERLAP=1: the driver's mv_overlap_comm_comp=1 branch (driver.hpp:278-282)
+  if (std::getenv("REF_DUMP_OVERLAP") != 0 && std::atoi(std::getenv("REF_DUMP_OVERLAP")) != 0) ref_rearrange_matrix_local_external(P);
   if (max_iter > 0) {
     std::vector<double> nh(max_iter + 1, -1.0), rh(max_iter + 1, -1.0), ph(max_iter + 1, -1.0), ah(max_iter + 1, -1.0);
     int iters = 0; double normr = 0;

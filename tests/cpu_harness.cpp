@@ -203,6 +203,18 @@ void hs_element(int nx, int ny, int nz, int ex, int ey, int ez, double *K36, dou
                1.0 / (double)nx, 1.0 / (double)ny, 1.0 / (double)nz, K36, f8);
 }
 void hs_tables(double *grad192, double *psi64) { hex8_tables(grad192, psi64); }
+// the same element through the per-axis Jacobian tables of the fused assembly kernel (hex8_jacobian_column / hex8_element_tables)
+void hs_element_tables(int nx, int ny, int nz, int ex, int ey, int ez, double *K36, double *f8)
+{
+  double grad[192], psi[64], jt[3][24];
+  hex8_tables(grad, psi);
+  const int n[3] = { nx, ny, nz }, e[3] = { ex, ey, ez };
+  for (int axis = 0; axis < 3; ++axis) {
+    const double c0 = (double)e[axis] / (double)n[axis], h = 1.0 / (double)n[axis], c1 = c0 + h;
+    for (int g = 0; g < 8; ++g) hex8_jacobian_column(grad, g, axis, c0, c1, jt[axis] + 3 * g);
+  }
+  hex8_element_tables(grad, psi, jt[0], jt[1], jt[2], K36, f8);
+}
 
 // The exact-dot pipeline (k_chunk_sums -> k_dot_maps -> k_dot_walk) executed sequentially with the same per-thread
 // arithmetic and the same storage conventions (piece maps always stored, leaf maps only for dirty pieces).

@@ -46,6 +46,16 @@ def history_case(n):
     return dict(n=np.array([n] * 3), num_iters=h["num_iters"], final_normr=h["final_normr"], normr=h["normr"], pap=h["pap"], alpha=h["alpha"], crc_x=crc(r.x()))
 
 
+def overlap_case(n, npr):
+    """mv_overlap_comm_comp=1 (driver.hpp:278-282): rearrange_matrix_local_external + matvec_overlap change the summation
+    order of the rows that have external columns, hence the history."""
+    d = ref_dump_mpi(*n, npr, overlap=True)
+    out = dict(n=np.array(n), np=npr, normr=d["normr_hist"][0], pap=d["pap_hist"][0])
+    for r in range(npr):
+        out["crc_x_%d" % r] = crc(d["x"][r]); out["x_%d" % r] = d["x"][r]
+    return out
+
+
 def mpi_case(n, npr, imbalance=0):
     d = ref_dump_mpi(*n, npr, imbalance=imbalance)
     out = dict(n=np.array(n), np=npr)
@@ -74,6 +84,8 @@ def main():
     # boxes changed by the reference's own add_imbalance (load_imbalance percent), ref/src/driver.hpp:137-139
     for n, npr, imb in (((12, 12, 12), 8, 30), ((10, 9, 8), 4, 60), ((9, 14, 11), 6, 40)):
         np.savez_compressed(os.path.join(HERE, "mpi_%dx%dx%d_np%d_imb%d.npz" % (n + (npr, imb))), **mpi_case(n, npr, imb))
+    for n, npr in (((8, 8, 8), 8), ((20, 30, 40), 2), ((12, 10, 9), 4), ((5, 3, 7), 3)):
+        np.savez_compressed(os.path.join(HERE, "mpiov_%dx%dx%d_np%d.npz" % (n + (npr,))), **overlap_case(n, npr))
     if args.big:
         for n in (128, 256):
             np.savez_compressed(os.path.join(HERE, "history_%d.npz" % n), **history_case(n))

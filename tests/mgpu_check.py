@@ -125,6 +125,16 @@ def main():
         xdotp, _ = mf.time_kernels(A, b, xk, None, nk)
         wx, wxdotp = o.time_kernels(f, nk)
         check(np.array_equal(bits(xk.coefs), bits(wx[rank])) and bits(np.array([xdotp]))[0] == bits(np.array([wxdotp]))[0], "%s time_kernels" % size)
+        # mv_overlap_comm_comp=1 (driver.hpp:278-282): rearrange_matrix_local_external + matvec_overlap, against what the
+        # UNMODIFIED reference computes on that branch (tests/golden/mpiov_*.npz)
+        gov = os.path.join(ROOT, "tests", "golden", "mpiov_%dx%dx%d_np%d.npz" % (n + (world,)))
+        if gold_boxes is None and os.path.exists(gov):
+            gv = np.load(gov)
+            mf.rearrange_matrix_local_external(A)
+            x2 = mf.Vector(first, A.num_rows())
+            it2, _, _, h2 = mf.cg_solve(A, b, x2, mf.matvec_overlap(), 200, EPS, history=True)
+            check(it2 == len(gv["normr"]) - 1 and np.array_equal(bits(h2["normr"]), bits(gv["normr"])), "%s overlap-order residual history" % size)
+            check(np.array_equal(bits(x2.coefs), bits(gv["x_%d" % rank])), "%s overlap-order solution" % size)
         if rank == 0:
             rel = np.abs(h["normr"][:k + 1] - want["normr"][:k + 1]) / np.maximum(want["normr"][:k + 1], 1e-300)
             print("size %s np=%d: iters %d (oracle %d), final resid %.6g, max rel diff of history %.3g" % (size, world, iters, want["num_iters"], normr, rel.max()), flush=True)

@@ -189,6 +189,12 @@ class Oracle:
         self.L.mfo_matvec(self.h, r, np.ascontiguousarray(x, np.float64), y)
         return y
 
+    def rearrange_matrix_local_external(self):
+        """ref/src/SparseMatrix_functions.hpp:319-408: from here on matvec / cg_solve sum the rows as matvec_overlap does"""
+        self.L.mfo_rearrange_matrix_local_external.argtypes = [C.c_void_p]
+        self.L.mfo_rearrange_matrix_local_external(self.h)
+        return self
+
     def time_kernels(self, f, max_iter):
         """ref/src/time_kernels.hpp:97-124 on every rank, with x_global[row] = f(row) on entry: p = 1*x + 0*x (+ the halo
         exchange), max_iter x matvec(A, p, x), xdotp = sum over max_iter x dot(x, p) (rank-ordered global sums).
@@ -370,12 +376,15 @@ _DUMP_INT = ("rows", "row_offsets", "cols_global", "cols_local", "box", "num_col
 _DUMP_F64 = ("coefs_prebc", "b_prebc", "coefs", "b", "normr_hist", "pap_hist", "x")
 
 
-def ref_dump_mpi(nx, ny, nz, nranks, max_iter=200, timeout=600, imbalance=0):
+def ref_dump_mpi(nx, ny, nz, nranks, max_iter=200, timeout=600, imbalance=0, overlap=False):
     """Run the unmodified reference on `nranks` ranks (MPI shim) and return {name: [per-rank arrays]}.
-    imbalance > 0: the reference's add_imbalance(load_imbalance = imbalance percent) changes the boxes first."""
+    imbalance > 0: the reference's add_imbalance(load_imbalance = imbalance percent) changes the boxes first.
+    overlap: the driver's mv_overlap_comm_comp=1 branch (rearrange_matrix_local_external + matvec_overlap)."""
     sys.path.insert(0, os.path.join(ORACLE_DIR, "mpi_shim"))
     import launch  # noqa
     out = {}
+    os.environ["REF_DUMP_OVERLAP"] = "1" if overlap else "0"
+    os.environ["REF_DUMP_LEAN"] = "0"
     with tempfile.TemporaryDirectory() as d:
         rc = launch.launch(nranks, [REF_DUMP, str(nx), str(ny), str(nz), d, str(max_iter)] + ([str(imbalance)] if imbalance else []),
                            timeout=timeout, stdout=subprocess.DEVNULL)

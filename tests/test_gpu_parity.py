@@ -399,6 +399,37 @@ def test_two_pass_matvec_of_every_rank_bit_exact(n, npr, oracle_built, product_l
         p.mesh.close()
 
 
+@pytest.mark.parametrize("n,npr", [((8, 8, 8), 8), ((20, 30, 40), 2), ((12, 10, 9), 4), ((5, 3, 7), 3)])
+def test_rearranged_matrix_sums_rows_like_matvec_overlap(n, npr, oracle_built, product_lib):
+    """mv_overlap_comm_comp=1 (driver.hpp:278-282): rearrange_matrix_local_external + matvec_overlap
+    (SparseMatrix_functions.hpp:319-408, 624-675) add a row's external entries AFTER its local ones, which changes the
+    rounding of the boundary rows.  mfe_rearrange_matrix_local_external re-sorts the rows on the device; the SpMV of every
+    rank (halo supplied by the caller) must then equal the oracle's re-arranged matvec bit for bit -- the oracle's
+    re-arrangement itself is pinned against the UNMODIFIED reference's overlap run (tests/golden/mpiov_*.npz,
+    test_oracle_vs_ref.py) -- and must differ from the storage-order result somewhere."""
+    o = Oracle(*n, npr).setup()
+    plain = [o.matvec(np.random.default_rng(5 + r).standard_normal(o.num_cols(r)), r) for r in range(npr)]
+    o.rearrange_matrix_local_external()
+    differs = False
+    for r in range(npr):
+        p = Problem(*n, nranks=npr, rank=r).setup()
+        x = np.random.default_rng(5 + r).standard_normal(p.A.num_cols)
+        mf.rearrange_matrix_local_external(p.A)
+        p.mesh.set_option("test_no_exchange", 1)
+        want = o.matvec(x, r)
+        differs = differs or not np.array_equal(bits(want), bits(plain[r]))
+        for overlap in (0, 1, 2):
+            p.mesh.set_option("overlap", overlap)
+            y = np.zeros(p.A.num_rows())
+            mf.matvec_overlap()(p.A, x.copy(), y)
+            assert_bits(y, want, "rank %d overlap %d" % (r, overlap))
+        rows, ro, cols, coefs = o.csr(r)
+        assert np.array_equal(p.A.packed_cols, cols)
+        assert_bits(p.A.packed_coefs, coefs, "re-sorted coefficients of rank %d" % r)
+        p.mesh.close()
+    assert differs, "the overlap order should change some row sums"
+
+
 import glob as _glob
 import os as _os
 _IMB = sorted(_glob.glob(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "mpi_*_imb*.npz")))
@@ -431,6 +462,25 @@ def test_boxes_changed_by_add_imbalance(path, oracle_built, product_lib):
             y = np.zeros(p.A.num_rows())
             mf.matvec(p.A, x.copy(), y)
             assert_bits(y, o.matvec(x, r), "rank %d matvec overlap %d" % (r, overlap))
+        p.mesh.close()
+
+
+@pytest.mark.parametrize("n,npr", [((5, 3, 7), 1), ((20, 30, 40), 1), ((33, 17, 40), 1), ((40, 24, 24), 2), ((33, 50, 17), 4), ((18, 18, 18), 8)])
+def test_fused_assembly_kernel_bit_exact(n, npr, oracle_built, product_lib):
+    """assembly_mode 1: k_assemble_fused keeps the element matrices in shared memory (two-plane ring, per-axis Jacobian
+    tables) instead of the scratch slab in global memory; A and b before and after the Dirichlet conditions must be the
+    oracle's bits on every rank (ref/src/perform_element_loop.hpp:40-104, SparseMatrix_functions.hpp:183-255)."""
+    o_pre = Oracle(*n, npr).setup(upto="assembly")
+    o = Oracle(*n, npr).setup()
+    for r in range(npr):
+        p = Problem(*n, nranks=npr, rank=r).structure()
+        p.mesh.set_option("assembly_mode", 1)
+        p.assemble()
+        assert_bits(p.A.packed_coefs, o_pre.csr(r)[3], "rank %d A before BC" % r)
+        assert_bits(p.b.coefs, o_pre.b(r), "rank %d b before BC" % r)
+        p.bc()
+        assert_bits(p.A.packed_coefs, o.csr(r)[3], "rank %d A" % r)          # make_local_matrix changes columns only
+        assert_bits(p.b.coefs, o.b(r), "rank %d b" % r)
         p.mesh.close()
 
 

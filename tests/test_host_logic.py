@@ -32,6 +32,7 @@ def H(harness):
     h.hs_get_csr.argtypes = [C.c_void_p] * 6
     h.hs_get_map.restype = C.c_longlong; h.hs_get_map.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
     h.hs_element.argtypes = [C.c_int] * 6 + [f64p, f64p]
+    h.hs_element_tables.argtypes = [C.c_int] * 6 + [f64p, f64p]
     h.hs_tables.argtypes = [f64p, f64p]
     h.hs_exact_dot.restype = C.c_double; h.hs_exact_dot.argtypes = [C.c_longlong, f64p, f64p, C.c_void_p]
     h.hs_serial_dot.restype = C.c_double; h.hs_serial_dot.argtypes = [C.c_longlong, f64p, f64p]
@@ -61,6 +62,10 @@ def test_element_tables_and_matrices(H, oracle_built):
             H.hs_element(*n, ex, ey, ez, K, f)
             _, _, Ko, fo = Oracle.element(*n, e)
             assert beq(K, Ko) and beq(f, fo), (n, e)
+            # the fused assembly kernel's formulation: Jacobian columns from per-axis tables (hex8_jacobian_column)
+            Kt, ft = np.zeros(36), np.zeros(8)
+            H.hs_element_tables(*n, ex, ey, ez, Kt, ft)
+            assert beq(Kt, Ko) and beq(ft, fo), ("tables", n, e)
     # unit cube and the h = 1/256 origin element of the reference
     K, f = np.zeros(36), np.zeros(8)
     H.hs_element(1, 1, 1, 0, 0, 0, K, f)

@@ -170,6 +170,33 @@ def test_oracle_equals_reference_multirank(n, npr, oracle_built):
         assert beq(o.x(r), d["x"][r])
 
 
+@pytest.mark.parametrize("n,npr", [((8, 8, 8), 8), ((20, 30, 40), 2), ((12, 10, 9), 4), ((5, 3, 7), 3)])
+def test_oracle_rearranged_matvec_equals_reference_overlap_golden(n, npr, oracle_built):
+    """mv_overlap_comm_comp=1: the golden files hold what the UNMODIFIED reference computes with
+    rearrange_matrix_local_external + matvec_overlap (ref_dump_mpi.x, REF_DUMP_OVERLAP=1); the oracle re-sorts its rows
+    instead (mfo_rearrange_matrix_local_external) and must reproduce history and solution bit for bit."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mpiov_%dx%dx%d_np%d.npz" % (n + (npr,))))
+    o = Oracle(*n, npr).setup()
+    o.rearrange_matrix_local_external()
+    h = o.cg_solve()
+    assert beq(h["normr"], g["normr"])
+    for r in range(npr):
+        assert beq(o.x(r), g["x_%d" % r])
+
+
+@pytest.mark.skipif(not have_ref_dump(), reason="oracle/_ref/ref_dump_mpi.x not built (needs /root/reference)")
+def test_oracle_rearranged_matvec_equals_reference_overlap_live(oracle_built):
+    n, npr = (7, 6, 9), 4
+    d = ref_dump_mpi(*n, npr, overlap=True)
+    o = Oracle(*n, npr).setup()
+    o.rearrange_matrix_local_external()
+    h = o.cg_solve()
+    assert beq(h["normr"], d["normr_hist"][0])
+    for r in range(npr):
+        assert beq(o.x(r), d["x"][r])
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference at build time)")
 @pytest.mark.parametrize("n,whole", [((10, 10, 10), False), ((6, 5, 7), True), ((20, 20, 20), False)])
 def test_verify_solution_vs_reference(n, whole, oracle_built):

@@ -4,19 +4,19 @@ import argparse, ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minife_b200 as mf
-ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=256); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--fold", type=int, default=1); ap.add_argument("--warps", type=int, default=0)
+ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=256); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--fold", type=int, default=1); ap.add_argument("--warps", type=int, default=0); ap.add_argument("--version", type=int, default=0)
 args = ap.parse_args()
 n = args.nx
 g = mf.Box([0, n, 0, n, 0, n]); mesh = mf.simple_mesh_description(g, g)
 A = mf.CSRMatrix(); mf.generate_matrix_structure(mesh, A); mf.assemble_FE_data(mesh, A, None)
 mf.impose_dirichlet(0.0, A, None, bc_rows=0); mf.impose_dirichlet(1.0, A, None, bc_rows=1); mf.make_local_matrix(A)
-mesh.set_option('dot_fold', args.fold); mesh.set_option('dot_maps_warps', args.warps)
+mesh.set_option('dot_maps_warps', args.warps); mesh.set_option('dot_maps_version', args.version); mesh.set_option('x_overlap', 0)
 L = mf.lib(); st = np.zeros(16 + 1024, np.uint64)
 L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 1)
 it, nr, t = mf.cg_solve(A, None, None, None, args.iters, 2.2e-16)
 L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 0)
 print("nx", n, "iters", it, "dots", int(st[0]), "dirty sum/max", int(st[1]), int(st[2]), "full replays", int(st[3]), "slow gaps", int(st[4]),
-      "walk ms total/max", st[5] / 1e6, st[6] / 1e6, "slowest dot #", int(st[7]), "cg DOT_s", t[1], "TOTAL_s", t[4])
+      "walk ms total/max", st[5] / 1e6, st[6] / 1e6, "slowest dot #", int(st[7]), "slow pieces", int(st[8]), "cg DOT_s", t[1], "TOTAL_s", t[4])
 for i in range(min(int(st[0]), 40)):
     w = int(st[16 + 2 * i])
     try:
