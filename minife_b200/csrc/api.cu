@@ -161,6 +161,8 @@ struct mfe_ctx {
   PeerComm peer;
   int comm_mode = 1;             // 1: NVLink peer stores when available (default), 0: NCCL send/recv + allgather
   int overlap = 1;               // peer mode: interior SpMV tiles run while the halo is in flight
+  int dbg_no_ext = 0;
+  int mv_ring = 1;
   int test_no_exchange = 0;      // test hook: skip the halo exchange (the caller supplies the externals), keep the two SpMV passes
   int ell_width = 0;             // > 0: the matrix stands for the reference's ELLMatrix of that row width (padding terms in the SpMV)
   int fused = 0;                 // MINIFE_FUSED reporting: SpMV + dot(Ap,p) are timed as MATVECDOT (cg_solve.hpp:172-176)
@@ -568,7 +570,7 @@ extern "C" int mfe_generate_matrix_structure(mfe_ctx *c, int64_t *nrows, int64_t
   c->num_cols = 0;
   if (dev_alloc(&c->d_rows, c->nrows) || dev_alloc(&c->d_roff, c->nrows + 8) || dev_alloc(&c->d_cols, c->nnz_padded) ||
       dev_alloc(&c->d_coefs, c->nnz_padded)) return 1;
-  CK(cudaMemsetAsync(c->d_cols, 0, c->nnz_padded * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->d_cols + c->nnz, 0, (c->nnz_padded - c->nnz) * sizeof(int), c->stream));      // the padding tail; k_structure writes every real entry
   CK(cudaMemsetAsync(c->d_coefs, 0, c->nnz_padded * sizeof(double), c->stream));   // MatrixInitOp.hpp:147 coefs = 0
   k_structure<<<grid_for(c->nrows, 128), 128, 0, c->stream>>>(c->m, c->d_rows, c->d_roff, c->d_cols);
   c->launches++;
@@ -821,8 +823,14 @@ static int launch_matvec_cfg(mfe_ctx *c, const MvArgs &a, int mode)
 }
 
 // one SpMV launch over this rank's matrix in the given mode (no halo exchange here except inside MV_FUSED)
-static int launch_matvec_local(mfe_ctx *c, const MvArgs &a, int mode)
+static int launch_matvec_local(mfe_ctx *c, const MvArgs &a_in, int mode)
 {
+  // p.Ap prediction sums: the single-GPU pass reduces each round (= one 512-row piece) in shared memory; the interior pass
+  // of a multi-rank SpMV uses one global atomic per tile instead -- measured on the 400x400x200 share of a 2-rank 400^3 run:
+  // the shared-memory ring couples the 16 warps of a CTA to within 8 rounds of each other and cost the fused kernel 35 %
+  // (2.17 vs 1.60 ms) where the tile costs vary more
+  MvArgs a = a_in;
+  a.use_ring = (c->mv_ring && mode == MV_ALL) ? 1 : 0;
   switch (c->mv_cfg) {
     case 0: return launch_matvec_cfg<16, 1, 2>(c, a, mode);
     case 1: return launch_matvec_cfg<16, 1, 1>(c, a, mode);
@@ -840,7 +848,7 @@ static MvArgs mv_args(mfe_ctx *c, const double *x, double *y, bool with_sums, co
   a.tile_base = c->d_tile_base; a.tile_base_flagged = c->d_tile_base_flagged;
   a.x = x; a.y = y; a.nrows = c->nrows; a.ntiles = c->ntiles; a.nnz_padded = c->nnz_padded; a.zmask = 0;
   a.piece_sums = with_sums ? c->dot.piece_sums_b : nullptr; a.chunk_sums = with_sums ? c->dot.chunk_sums_b : nullptr;
-  a.gate = gate; a.k = k; a.tile_list = c->d_tiles_boundary; a.nlist = c->n_boundary; a.ell_width = c->ell_width; a.seed_y = seed_y ? 1 : 0;
+  a.gate = gate; a.k = k; a.tile_list = c->d_tiles_boundary; a.nlist = c->n_boundary; a.ell_width = c->ell_width; a.seed_y = seed_y ? 1 : 0; a.use_ring = c->mv_ring;
   return a;
 }
 
@@ -927,6 +935,7 @@ static int launch_matvec(mfe_ctx *c, double *x, double *y, bool with_sums, const
   const bool two_sets = c->n_interior > 0 && c->n_boundary > 0;
   if ((use_peer(c) || (c->test_no_exchange && c->nranks > 1)) && c->overlap == 1 && two_sets) {
     a.halo = x + c->nrows;                                  // test hook: the caller supplied the externals in the tail of x
+    a.dbg_no_ext = c->test_no_exchange ? c->dbg_no_ext : 0;
     if (use_peer(c) && !c->test_no_exchange) {
       if (!c->comm) return fail("matvec: nranks > 1 but mfe_comm_init was not called");
       const unsigned long long epoch = ++c->peer.halo_epoch;
@@ -1378,6 +1387,8 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   if (!strcmp(name, "assembly_mode")) { c->assembly_mode = value != 0; return 0; }
   if (!strcmp(name, "dot_maps_version")) { c->dot_maps_version = value != 0; return 0; }
   if (!strcmp(name, "test_no_exchange")) { c->test_no_exchange = value != 0; return 0; }
+  if (!strcmp(name, "dbg_no_ext")) { c->dbg_no_ext = (int)value; return 0; }
+  if (!strcmp(name, "mv_ring")) { c->mv_ring = value != 0; return 0; }
   if (!strcmp(name, "ell_width")) {          // ref/src/ELLMatrix.hpp: 0 = CSR semantics, 27 = the width generate_matrix_structure reserves
     if (value < 0 || value > 64) return fail("mfe_set_option: ell_width must be in [0,64]");
     c->ell_width = (int)value;
@@ -1595,6 +1606,7 @@ extern "C" int mfe_time_kernel(mfe_ctx *c, const char *what, int reps, double *m
   auto body = [&](int rep) -> int {
     if (!strcmp(what, "matvec")) return launch_matvec_local(c, mv_args(c, c->d_p, c->d_Ap, false, nullptr, 0, false), MV_ALL);
     if (!strcmp(what, "matvec_dot")) return launch_matvec_local(c, mv_args(c, c->d_p, c->d_Ap, true, nullptr, 0, false), MV_ALL);
+    if (!strcmp(what, "matvec_op")) return launch_matvec(c, c->d_p, c->d_Ap, true, nullptr, 0, false, false);   // incl. exchange / overlap mode (honours test_no_exchange)
     if (!strcmp(what, "matvec_simple")) { k_matvec_simple<<<grid_for(n, 128), 128, 0, c->stream>>>(c->d_coefs, c->d_cols, c->d_roff, c->d_tile_base, c->tr, c->d_p, c->d_Ap, n, c->ell_width); c->launches++; return 0; }
     if (!strcmp(what, "stream_probe")) {
       constexpr int PG = 16, PS = 1;

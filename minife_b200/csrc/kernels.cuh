@@ -73,17 +73,32 @@ __device__ inline void cg_epilogue(CgScalars *s, int epi, int k, double dot, dou
 __global__ void __launch_bounds__(128) k_structure(MeshDesc m, int *__restrict__ rows, uint32_t *__restrict__ roff,
                                                    int *__restrict__ cols)
 {
+  // the columns of a warp's 32 consecutive rows are one contiguous run of packed_cols: staged in shared memory, then
+  // written with consecutive lanes on consecutive addresses (see k_gather_rows)
+  __shared__ int sbuf[4][32 * 27];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lr >= m.nrows) return;
-  int ix, iy, iz;
-  local_row_to_node(m, lr, ix, iy, iz);
-  const int64_t off = row_offset_of(m, ix, iy, iz);
-  rows[lr] = m.first_row + (int)lr;
-  roff[lr] = (uint32_t)off;
-  int c[27]; unsigned char s[27];
-  const int len = row_columns(m, ix, iy, iz, c, s);
-  for (int j = 0; j < len; ++j) cols[off + j] = c[j];
-  if (lr == m.nrows - 1) roff[m.nrows] = (uint32_t)(off + len);
+  const bool active = lr < m.nrows;
+  int64_t off = 0;
+  int len = 0;
+  if (active) {
+    int ix, iy, iz;
+    local_row_to_node(m, lr, ix, iy, iz);
+    off = row_offset_of(m, ix, iy, iz);
+    rows[lr] = m.first_row + (int)lr;
+    roff[lr] = (uint32_t)off;
+    int c[27]; unsigned char s[27];
+    len = row_columns(m, ix, iy, iz, c, s);
+    const int rel = (int)(off - __shfl_sync(__activemask(), off, 0));
+    for (int j = 0; j < len; ++j) sbuf[wq][rel + j] = c[j];
+    if (lr == m.nrows - 1) roff[m.nrows] = (uint32_t)(off + len);
+  }
+  __syncwarp();
+  const int64_t woff = __shfl_sync(0xffffffffu, off, 0);
+  int total = active ? (int)(off - woff) + len : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
+  for (int i = lane; i < total; i += 32) cols[woff + i] = sbuf[wq][i];
 }
 
 // per-tile 64-bit nnz offsets for the SpMV (tile = TR consecutive rows), structured mesh
@@ -178,20 +193,36 @@ __global__ void __launch_bounds__(128) k_gather_rows(MeshDesc m, ElemSlab sl, co
                                                      const uint32_t *__restrict__ roff, const int64_t *__restrict__ tile_base, int tr,
                                                      double *__restrict__ coefs, double *__restrict__ b)
 {
+  // The 32 rows of a warp are consecutive, so their coefficients are one contiguous run of the CSR array: they are staged in
+  // shared memory at their final relative positions and written out with consecutive lanes on consecutive addresses (a
+  // thread storing its own 27 values writes with a 216-byte stride between lanes: 4x the store transactions).
+  __shared__ double sbuf[4][32 * 27];
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
   const int64_t plane = (int64_t)m.lnx * m.lny;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= plane * (iz1 - iz0)) return;
-  const int64_t lr = (int64_t)(iz0 - m.nb[4]) * plane + idx;
-  int ix, iy, iz;
-  local_row_to_node(m, lr, ix, iy, iz);
-
-  double acc[27], bsum;
-  gather_row(m, sl, KF, ix, iy, iz, acc, bsum);
-  // nnz offset of this row: 64-bit tile base + 32-bit in-tile difference
-  const int64_t t = lr / tr;
-  const int64_t off = tile_base[t] + (int64_t)(uint32_t)(roff[lr] - roff[t * tr]);
-  b[lr] = bsum;
-  store_row(m, ix, iy, iz, off, acc, coefs);
+  const bool active = idx < plane * (iz1 - iz0);
+  int64_t off = 0;
+  int len = 0;
+  if (active) {
+    const int64_t lr = (int64_t)(iz0 - m.nb[4]) * plane + idx;
+    int ix, iy, iz;
+    local_row_to_node(m, lr, ix, iy, iz);
+    double acc[27], bsum;
+    gather_row(m, sl, KF, ix, iy, iz, acc, bsum);
+    // nnz offset of this row: 64-bit tile base + 32-bit in-tile difference
+    const int64_t t = lr / tr;
+    off = tile_base[t] + (int64_t)(uint32_t)(roff[lr] - roff[t * tr]);
+    len = (int)(uint32_t)(roff[lr + 1] - roff[lr]);
+    b[lr] = bsum;
+    const int64_t woff = __shfl_sync(__activemask(), off, 0);
+    store_row(m, ix, iy, iz, off - woff, acc, sbuf[wq]);
+  }
+  __syncwarp();
+  const int64_t woff = __shfl_sync(0xffffffffu, off, 0);          // lane 0 is active whenever any lane of the warp is
+  int total = active ? (int)(off - woff) + len : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
+  for (int i = lane; i < total; i += 32) coefs[woff + i] = sbuf[wq][i];
 }
 
 // ------------------------------------------------------------------------------------------------------

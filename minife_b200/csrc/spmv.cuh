@@ -63,6 +63,8 @@ struct MvArgs {                      // by-value kernel argument
   const CgScalars *gate; int k;
   const int *tile_list; int64_t nlist;   // MV_LIST / MV_FUSED: the boundary tiles
   int ell_width;
+  int use_ring;                      // 1: per-round piece sums reduced in shared memory (ring of 8 rounds), 0: one global atomic per tile
+  int dbg_no_ext;                    // measurement hook: boundary pass reads the externals from the tail of x (test_no_exchange only)
   int seed_y;                        // 1: the caller's y is meaningful (API call): beta*y[row] is formed for every row
   // MV_FUSED only
   const double *halo;                // externals of this epoch: column c >= nrows reads halo[c - nrows]
@@ -253,7 +255,7 @@ __device__ __forceinline__ bool mv_pass(const MvArgs &a, const MvSmem &sm, uint3
       int64_t t2;
       if (item(j + S, t2)) issue(t2, s);
       if (piece_sums) {               // rows [32 t, 32 t + 32) lie in piece t / 16 and in chunk t / 128
-        if (G == 16 && PASS != MV_LIST) {
+        if (G == 16 && PASS != MV_LIST && a.use_ring) {
           // the 16 tiles of one round of this CTA are exactly one piece: reduce them in shared memory (ring of 8
           // rounds; the warp that completes a round publishes it and hands the slot to round j + 8).  A warp that is
           // 8 rounds ahead of a straggler waits for the slot (the straggler never waits for a later round, so this
@@ -345,7 +347,7 @@ k_matvec(const __grid_constant__ MvArgs a)
   }
   // (2) the tiles that need no external
   mv_pass<G, S, H, MV_SKIP, false>(a, sm, phase_bits, pol_stream, false);
-  if (a.nlist <= 0) return;
+  if (a.nlist <= 0 || a.dbg_no_ext == 2) return;
   // (3) Irecv ... Wait (exchange_externals.hpp:90-101, 147-153): every warp checks the neighbours' flags itself
   if (a.pw.n > 0) {
     bool ok = true;
@@ -358,7 +360,8 @@ k_matvec(const __grid_constant__ MvArgs a)
     }
   }
   // (4) the boundary tiles (their prediction sums go through atomics, not through the ring of round sums)
-  mv_pass<G, S, H, MV_LIST, true>(a, sm, phase_bits, pol_stream, false);
+  if (a.dbg_no_ext) mv_pass<G, S, H, MV_LIST, false>(a, sm, phase_bits, pol_stream, false);
+  else mv_pass<G, S, H, MV_LIST, true>(a, sm, phase_bits, pol_stream, false);
 }
 
 // Streaming probe (measurement only): the staging half of k_matvec with the consumer removed -- every warp waits

@@ -159,7 +159,7 @@ def test_multi_rank_dropin_dumps_identical_to_reference(nproc, args):
         with open(os.path.join(a, "stdout.txt"), "w") as fa:
             assert launch.launch(nproc, [OURS_NP] + args, cwd=a, timeout=900, stdout=fa) == 0, open(os.path.join(a, "stdout.txt")).read()[-2000:]
         with open(os.path.join(b, "stdout.txt"), "w") as fb:
-            assert launch.launch(nproc, [REF_NP] + [x for x in args if not x.startswith("mv_overlap")], cwd=b, timeout=900, stdout=fb) == 0
+            assert launch.launch(nproc, [REF_NP] + args, cwd=b, timeout=900, stdout=fb) == 0
         names = sorted(os.path.basename(p) for p in glob.glob(os.path.join(b, "*.mtx.*")) + glob.glob(os.path.join(b, "*.vec.*")))
         assert len(names) >= 7 * nproc, names
         for n in names:
