@@ -56,48 +56,82 @@ def algorithmic_bytes(nrows, nnz, iters):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons of one GPU DURING the timed region (B200_PROFILING.md recipe).  Sampled through
+    NVML inside this process (a thread, one sample per 250 ms; no child process polling the driver).  Falls back to an
+    `nvidia-smi -lms 500` child without pynvml."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period=0.25):
+        self.index, self.rows, self.proc, self.period, self.how = index, [], None, period, None
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, nv, h):
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.rows.append((float(sm), float(self.max_sm), pw, [n for n, bit in names if rs & bit]))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may remap the CUDA index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.how = "nvml"
+            self.t = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.how = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "500"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
 
     def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                self.rows.append((float(r[1]), float(r[2]), float(r[3]), [nm for nm, v in zip(names, r[5:9]) if v.lower().startswith("active")]))
             except (ValueError, IndexError):
                 continue
-            for nm, v in zip(names, r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        self._stop.set()
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        try:
+            self.t.join(timeout=2)
+        except Exception:
+            pass
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "how": self.how}
+        sm = [r[0] for r in self.rows]; mx = [r[1] for r in self.rows]; pw = [r[2] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[3]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)), "samples": len(sm), "reasons": reasons,
+                "how": "%s, one sample per %.0f ms during the timed solves" % (self.how, 1e3 * self.period if self.how == "nvml" else 500)}
 
 
 def measured_peaks():
@@ -400,12 +434,29 @@ def main():
                 "note": "one untimed solve with CUDA events around every op (costs ~3 %); the timed solves record events around the SpMV only"}
     mesh.set_op_timing(args.op_timing)
     launches0 = mesh.launch_count()
+    L.mfe_dot_stats(mesh._h, None, 0, 1)             # reset the dot diagnostics
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     dev_s, wall_s, mv_s, its, normr = timed(False, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = mesh.launch_count() - launches0
+    # exact-dot diagnostics of the timed solves (mfe_dot_stats): walk time and, multi-rank, the time spent in the all-reduce
+    st = np.zeros(16, np.uint64)
+    L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), 16, 0)
+    ndots = max(int(st[0]), 1)
+    dstat = torch.tensor([float(st[5]) / ndots / 1e3, float(st[9]) / ndots / 1e3, float(st[10]) / 1e3, float(st[1]) / ndots, float(st[4]), float(st[8]) / ndots,
+                          float(t1[0]), float(t1[1]), float(t1[2])], dtype=torch.float64, device="cuda")
+    if dist:
+        allst = [torch.zeros_like(dstat) for _ in range(world)]
+        dist.all_gather(allst, dstat)
+    else:
+        allst = [dstat]
+    dot_diag = {"per_rank_walk_us": [round(float(t[0]), 2) for t in allst], "per_rank_allreduce_wait_us_avg": [round(float(t[1]), 2) for t in allst],
+                "per_rank_allreduce_wait_us_max": [round(float(t[2]), 1) for t in allst], "per_rank_dirty_leaves_avg": [round(float(t[3]), 1) for t in allst],
+                "slow_gaps": [int(t[4]) for t in allst], "per_rank_slow_pieces_per_dot": [round(float(t[5]), 1) for t in allst],
+                "per_rank_op_timed_solve_s": {"WAXPY": [round(float(t[6]), 5) for t in allst], "DOT": [round(float(t[7]), 5) for t in allst],
+                                              "MATVEC": [round(float(t[8]), 5) for t in allst]}}
     e_dev, e_wall, _, e_its, _ = timed(True, max(1, min(args.steps, 3)))
 
     iters = its[-1]
@@ -463,6 +514,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * nrows, "d2h_bytes_per_step": 8 * nrows + 4 * 8 * (MAX_ITERS + 1) + 128,
                     "ms_per_step": e2e_t * 1e3, "what": "mfe_cg_solve with host x (pinned): H2D x0 + 200-iteration solve + D2H x and histories, wall clock, max over ranks"},
             "gpu_launches": int(launches),
+            "dot_diag": dot_diag,
             "roofline": roofline,
             "assembly": assembly,
             "parity": parity,

@@ -576,7 +576,8 @@ extern "C" int mfe_generate_matrix_structure(mfe_ctx *c, int64_t *nrows, int64_t
   c->launches++;
   CK(cudaGetLastError());
   if (build_tile_base(c)) return 1;
-  if (ensure_vectors(c, c->nrows, c->nrows)) return 1;
+  // sized for the external tail make_local_matrix will add (bounded by the one-node shell), so nothing is reallocated later
+  if (ensure_vectors(c, c->nrows, c->nrows + (c->nranks > 1 ? halo_cap_of(c->boxes[c->rank]) : 0))) return 1;
   // Vector b, x are zero-filled on construction (Vector.hpp:44-52, driver.hpp:188-189)
   CK(cudaMemsetAsync(c->d_b, 0, c->vec_cap * 8, c->stream));
   CK(cudaMemsetAsync(c->d_x, 0, c->vec_cap * 8, c->stream));
@@ -990,8 +991,9 @@ static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const dou
 static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double *y, const DotWork &w, const CgScalars *gate, int k)
 {
   if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail("dot: operands must be 16-byte aligned");
-  const int nw = c->dot_maps_warps ? c->dot_maps_warps : 24;
-  if (x == y) return nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k);
+  int nw = c->dot_maps_warps ? c->dot_maps_warps : 24;
+  if (nw == 32 && (x != y || c->dot_maps_version == 1)) nw = 24;
+  if (x == y) return nw == 32 ? launch_dot_maps_cfg<true, 32>(c, n, x, y, w, gate, k) : nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k);
   return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k);
 }
 
@@ -1368,7 +1370,7 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
     return 0;
   }
   if (!strcmp(name, "dot_maps_warps")) {
-    if (value != 0 && value != 16 && value != 24) return fail("mfe_set_option: dot_maps_warps must be 0, 16 or 24");
+    if (value != 0 && value != 16 && value != 24 && value != 32) return fail("mfe_set_option: dot_maps_warps must be 0, 16, 24 or 32 (32: x.x dots only)");
     c->dot_maps_warps = (int)value;
     return 0;
   }

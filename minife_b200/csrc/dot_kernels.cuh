@@ -329,8 +329,13 @@ __device__ __noinline__ void dot_walk_body(int64_t n, const double *__restrict__
     }
   }
   bool ok = true;
+  const unsigned long long t_ar = (w.stats && tid == 0 && wa.pd.nranks > 1) ? global_ns() : 0ULL;
   if (wa.pd.nranks > 1) s = peer_dot_allreduce(wa.pd, s, ok);     // rank-ordered global sum over NVLink peer memory
   if (tid == 0) {
+    if (w.stats && wa.pd.nranks > 1) {          // [9] total / [10] max ns spent in the all-reduce (mostly: waiting for the slowest rank)
+      const unsigned long long dt = global_ns() - t_ar;
+      w.stats[9] += dt; if (dt > w.stats[10]) w.stats[10] = dt;
+    }
     *w.result = s;
     if (sc) {
       if (!ok) { sc->status = CG_COMM_ERROR; sc->stop_iter = -1; }
@@ -497,28 +502,48 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
     // ones].  Taken only when those bounds, applied to the predicted significand, stay MFE_DOT_FAR_MARGIN ulps inside
     // the binade (so dot_apply will accept the map); anything else -- a binade change, an exact tie, a huge term, the
     // ragged tail -- goes leaf by leaf through dot_piece_slow.
-    bool fast = (int64_t)(piece + 1) * DOT_PIECE <= n && hyp0 >= 0 && hyp0 != HYP_ZERO && hyp0 == dot_hyp_of(pre1) && kk <= 1023;
+    const bool whole = (int64_t)(piece + 1) * DOT_PIECE <= n;
+    bool fast = whole && hyp0 >= 0 && hyp0 != HYP_ZERO && hyp0 == dot_hyp_of(pre1) && kk <= 1023;
     mbar_wait(bar, parity);
     parity ^= 1u;
     DotMap wm;
     bool piece_dirty = false;
-    if (fast) {
+    if (whole && hyp0 == HYP_ZERO && dot_hyp_of(pre1) == HYP_ZERO) {
+      // The running sum is predicted to be exactly +0.0 before and after the piece (a Dirichlet face: the z = 0 plane of a
+      // rank is ~130 consecutive pieces of zeros, all in the range of ONE CTA -- through the leaf-by-leaf path they made that
+      // CTA the straggler of the kernel: +65 us per dot on the ranks at x = 0, z = 0 of a 2x2x2 run).  If every product is
+      // +-0.0 the sum stays +0.0: the zero map (exact_dot.h, HYP_ZERO).
+      const uint32_t lbase = smem_u32(stage + lane * DOT_LEAF), rotb = (uint32_t)(lane & (DOT_LEAF - 1)) * 8u;
+      bool allz = true;
+#pragma unroll
+      for (int i = 0; i < DOT_LEAF; ++i) {
+        const uint32_t ad = lbase | ((uint32_t)(i * 8) ^ rotb);
+        const double xv = lds_f64(ad);
+        allz = allz && dot_is_zero(SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(ad)));
+      }
+      if (__all_sync(0xffffffffu, allz)) { wm = dot_zero_map(); fast = true; }
+    } else if (fast) {
       const double c = ((hyp0 >> 11) & 1) ? -dot_pow2(kk) : dot_pow2(kk);
       double A[4] = { 0.0, 0.0, 0.0, 0.0 }, AB[4] = { 0.0, 0.0, 0.0, 0.0 };
       unsigned dm[4] = { 0, 0, 0, 0 }, sg = 0;
       // byte address of element i ^ rot of this lane's leaf (bank-conflict free; the leaf base is 128-byte aligned, so OR = ADD)
       const uint32_t lbase = smem_u32(stage + lane * DOT_LEAF), rotb = (uint32_t)(lane & (DOT_LEAF - 1)) * 8u;
-      // all loads first (the shared-memory loads are volatile asm: the compiler keeps them where they are written, and
-      // a load placed next to its use would expose its latency sixteen times), then the arithmetic
-      double pr[DOT_LEAF];
+      // loads in batches ahead of the arithmetic (the shared-memory loads are volatile asm: the compiler keeps them where
+      // they are written, and a load placed next to its use would expose its latency sixteen times); two batches of 8 when
+      // the register budget is 64 (NW = 32), one batch of 16 otherwise
+      constexpr int NB = NW > 24 ? 8 : DOT_LEAF;
 #pragma unroll
-      for (int i = 0; i < DOT_LEAF; ++i) {
-        const uint32_t ad = lbase | ((uint32_t)(i * 8) ^ rotb);
-        const double xv = lds_f64(ad);
-        pr[i] = SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(ad));
+      for (int i0 = 0; i0 < DOT_LEAF; i0 += NB) {
+        double pr[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+          const uint32_t ad = lbase | ((uint32_t)((i0 + i) * 8) ^ rotb);
+          const double xv = lds_f64(ad);
+          pr[i] = SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(ad));
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) MFE_DOT_SIMPLE_TERM((i0 + i) & 3, __dmul_rn(pr[i], c))
       }
-#pragma unroll
-      for (int i = 0; i < DOT_LEAF; ++i) MFE_DOT_SIMPLE_TERM(i & 3, __dmul_rn(pr[i], c))
       double asum = __dadd_rn(__dadd_rn(A[0], A[1]), __dadd_rn(A[2], A[3]));
       double absum = __dadd_rn(__dadd_rn(AB[0], AB[1]), __dadd_rn(AB[2], AB[3]));
       unsigned dmax = max(max(dm[0], dm[1]), max(dm[2], dm[3]));
@@ -537,7 +562,7 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
              (nonneg || (Sp + ng) - MFE_DOT_FAR_MARGIN > 4503599627370496.0) && (Sp + pos) + MFE_DOT_FAR_MARGIN < 9007199254740992.0;
       wm.a0 = (long long)asum; wm.a1 = wm.a0; wm.lo = nonneg ? 1LL : (long long)ng; wm.hi = (long long)pos; wm.hyp = hyp0; wm.pad = 0;
     }
-    if (!fast) wm = dot_piece_slow<SAME>(n, x, y, w, piece, stage, pre0, pre1, piece_dirty);
+    if (!fast) wm = dot_piece_slow<SAME>(n, x, y, w, piece, stage, pre0, pre1, piece_dirty);      // (also a zero-hypothesis piece with a nonzero term)
     __syncwarp();
     if (lane == 0 && j + NW < np) issue(piece + NW);           // the stage is free: next piece in flight while we publish
 

@@ -6,6 +6,7 @@
 // The peers' lists (-> elements_to_send) follow from the same rule applied to the peer's box.
 #pragma once
 #include <algorithm>
+#include <thread>
 #include <vector>
 #include "mesh.h"
 
@@ -36,12 +37,19 @@ inline void for_each_external(const MeshDesc &gm, int p, F fn)
   m.first_row = B.first_row; m.nrows = B.nrows;
   const int lo[3] = { std::max(B.nb[0] - 1, 0), std::max(B.nb[2] - 1, 0), std::max(B.nb[4] - 1, 0) };
   const int hi[3] = { std::min(B.nb[1] + 1, gm.gnx), std::min(B.nb[3] + 1, gm.gny), std::min(B.nb[5] + 1, gm.gnz) };
+  int last = p;                         // neighbouring shell nodes mostly share their owner: try the last one first
   auto add = [&](int x, int y, int z) {
     const int fx = std::max(B.nb[0], x - 1), fy = std::max(B.nb[2], y - 1), fz = std::max(B.nb[4], z - 1);
     const int64_t first = (int64_t)(fx - B.nb[0]) + (int64_t)m.lnx * ((fy - B.nb[2]) + (int64_t)m.lny * (fz - B.nb[4]));
-    int ox, oy, oz;
-    const int grow = node_to_row(m, x, y, z);
-    fn(first, grow, row_to_node(m, grow, ox, oy, oz));
+    // owner = the rank whose node box holds (x,y,z) (box_utils.hpp:233-315); global row = its first row + x-fastest index
+    auto inside = [&](const RankBox &b) { return x >= b.nb[0] && x < b.nb[1] && y >= b.nb[2] && y < b.nb[3] && z >= b.nb[4] && z < b.nb[5]; };
+    int q = last;
+    if (!inside(gm.boxes[q])) { for (q = 0; q < gm.nranks; ++q) if (inside(gm.boxes[q])) break; }
+    if (q >= gm.nranks) return;         // cannot happen for an in-range node of a partition that covers the mesh
+    last = q;
+    const RankBox &b = gm.boxes[q];
+    const int grow = b.first_row + (x - b.nb[0]) + (b.nb[1] - b.nb[0]) * ((y - b.nb[2]) + (b.nb[3] - b.nb[2]) * (z - b.nb[4]));
+    fn(first, grow, q);
   };
   for (int z = lo[2]; z < hi[2]; ++z)
     for (int y = lo[1]; y < hi[1]; ++y) {
@@ -55,13 +63,30 @@ inline void for_each_external(const MeshDesc &gm, int p, F fn)
 }
 
 inline bool ext_before(const ExtEntry &a, const ExtEntry &b) { return a.first != b.first ? a.first < b.first : a.grow < b.grow; }
+// (first, grow) packed into one sortable word: both are below 2^31 (int32 ordinals)
+inline uint64_t ext_key(int64_t first, int grow) { return ((uint64_t)first << 32) | (uint32_t)grow; }
+inline int owner_of_row(const MeshDesc &gm, int grow)
+{
+  int owner = 0;
+  for (int p = gm.nranks - 1; p >= 0; --p)
+    if (gm.boxes[p].nrows > 0 && gm.boxes[p].first_row <= grow) { owner = p; break; }     // make_local_matrix.hpp:135-143
+  return owner;
+}
 
 // externals of rank p in the reference's first-encounter order
 inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
 {
-  out.clear();
-  for_each_external(gm, p, [&](int64_t first, int grow, int owner) { out.push_back(ExtEntry{ first, grow, owner }); });
-  std::sort(out.begin(), out.end(), ext_before);
+  std::vector<uint64_t> keys;
+  const RankBox &B = gm.boxes[p];
+  keys.reserve((size_t)2 * ((int64_t)(B.nb[1] - B.nb[0] + 2) * (B.nb[3] - B.nb[2] + 2) + (int64_t)(B.nb[1] - B.nb[0] + 2) * (B.nb[5] - B.nb[4] + 2) +
+                            (int64_t)(B.nb[3] - B.nb[2] + 2) * (B.nb[5] - B.nb[4] + 2)));
+  for_each_external(gm, p, [&](int64_t first, int grow, int) { keys.push_back(ext_key(first, grow)); });
+  std::sort(keys.begin(), keys.end());
+  out.resize(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) {
+    const int grow = (int)(uint32_t)(keys[i] & 0xffffffffULL);
+    out[i] = ExtEntry{ (int64_t)(keys[i] >> 32), grow, owner_of_row(gm, grow) };
+  }
 }
 
 // What rank p receives from rank `me`, without sorting p's whole shell: its externals owned by `me` in p's encounter order
@@ -71,19 +96,22 @@ inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
 // first-encounter keys, one sort of my (small) group.
 inline void peer_wants_from(const MeshDesc &gm, int p, int me, std::vector<ExtEntry> &mine, int &dst_offset)
 {
-  mine.clear();
+  std::vector<uint64_t> keys;
   std::vector<int> cnt(gm.nranks, 0);
-  std::vector<ExtEntry> firstkey(gm.nranks, ExtEntry{ 0, 0, -1 });
+  std::vector<uint64_t> firstkey(gm.nranks, ~0ULL);
   for_each_external(gm, p, [&](int64_t first, int grow, int owner) {
-    const ExtEntry e{ first, grow, owner };
-    if (cnt[owner]++ == 0 || ext_before(e, firstkey[owner])) firstkey[owner] = e;
-    if (owner == me) mine.push_back(e);
+    const uint64_t k = ext_key(first, grow);
+    ++cnt[owner];
+    if (k < firstkey[owner]) firstkey[owner] = k;
+    if (owner == me) keys.push_back(k);
   });
-  std::sort(mine.begin(), mine.end(), ext_before);
+  std::sort(keys.begin(), keys.end());
+  mine.resize(keys.size());
+  for (size_t i = 0; i < keys.size(); ++i) mine[i] = ExtEntry{ (int64_t)(keys[i] >> 32), (int)(uint32_t)(keys[i] & 0xffffffffULL), me };
   dst_offset = 0;
   if (cnt[me] == 0) return;
   for (int q = 0; q < gm.nranks; ++q)
-    if (q != me && cnt[q] > 0 && ext_before(firstkey[q], firstkey[me])) dst_offset += cnt[q];
+    if (q != me && cnt[q] > 0 && firstkey[q] < firstkey[me]) dst_offset += cnt[q];
 }
 
 // group by owner in first-encounter order of owners, encounter order inside a group (make_local_matrix.hpp:153-166)
@@ -120,13 +148,21 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
   // what each neighbour needs from me, in ITS external order (make_local_matrix.hpp:386-429)
   L.send_length.assign(L.neighbors.size(), 0);
   L.send_dst_offset.assign(L.neighbors.size(), 0);
-  std::vector<ExtEntry> mine;
-  for (size_t i = 0; i < L.neighbors.size(); ++i) {
-    int poff = 0;
-    peer_wants_from(gm, L.neighbors[i], rank, mine, poff);
-    L.send_length[i] = (int)mine.size();
-    L.send_dst_offset[i] = poff;
-    for (const ExtEntry &e : mine) L.elements_to_send.push_back(e.grow - first_row);
+  // one pass over each neighbour's shell, independent of each other: a few host threads
+  const size_t nn = L.neighbors.size();
+  std::vector<std::vector<ExtEntry>> mine(nn);
+  std::vector<int> poff(nn, 0);
+  {
+    const size_t nthreads = std::min<size_t>(nn, 8);
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t]() { for (size_t i = t; i < nn; i += nthreads) peer_wants_from(gm, L.neighbors[i], rank, mine[i], poff[i]); });
+    for (std::thread &th : pool) th.join();
+  }
+  for (size_t i = 0; i < nn; ++i) {
+    L.send_length[i] = (int)mine[i].size();
+    L.send_dst_offset[i] = poff[i];
+    for (const ExtEntry &e : mine[i]) L.elements_to_send.push_back(e.grow - first_row);
   }
   L.num_cols = (int64_t)nrows + n_ext;
 }

@@ -15,7 +15,7 @@ echo "mgpu_check rc=$?" >> $O/r02_mgpu_check_n$N.log
 python -m pytest tests/test_gpu_dropin.py -q -k multi_rank > $O/r02_dropin_np_n$N.log 2>&1
 echo "dropin rc=$?" >> $O/r02_dropin_np_n$N.log
 $TR --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 > $O/r02_bench_n${N}_weak.json 2> $O/r02_bench_n${N}_weak.err
-$TR --master-port 29513 bench.py --gpus $N --steps 3 --warmup 3 --overlap 2 > $O/r02_bench_n${N}_weak_overlap2.json 2> $O/r02_bench_n${N}_weak_overlap2.err
+[ $N = 2 ] && $TR --master-port 29513 bench.py --gpus $N --steps 3 --warmup 3 --overlap 2 > $O/r02_bench_n${N}_weak_overlap2.json 2> $O/r02_bench_n${N}_weak_overlap2.err
 $TR --master-port 29514 bench.py --gpus $N --steps 3 --warmup 3 --strong --nx 400 > $O/r02_strong_400_n$N.json 2> $O/r02_strong_400_n$N.err
 $TR --master-port 29515 bench.py --gpus $N --steps 3 --warmup 3 --strong --nx 512 > $O/r02_strong_512_n$N.json 2> $O/r02_strong_512_n$N.err
 tail -3 $O/r02_mgpu_check_n$N.log; tail -2 $O/r02_dropin_np_n$N.log
