@@ -64,7 +64,7 @@ struct MvArgs {                      // by-value kernel argument
   const int *tile_list; int64_t nlist;   // MV_LIST / MV_FUSED: the boundary tiles
   int ell_width;
   int use_ring;                      // 1: per-round piece sums reduced in shared memory (ring of 8 rounds), 0: one global atomic per tile
-  int dbg_no_ext;                    // measurement hook: boundary pass reads the externals from the tail of x (test_no_exchange only)
+  int dbg_no_ext;                    // measurement hook (test_no_exchange only): 2 = leave after the interior pass
   int seed_y;                        // 1: the caller's y is meaningful (API call): beta*y[row] is formed for every row
   // MV_FUSED only
   const double *halo;                // externals of this epoch: column c >= nrows reads halo[c - nrows]
@@ -360,8 +360,7 @@ k_matvec(const __grid_constant__ MvArgs a)
     }
   }
   // (4) the boundary tiles (their prediction sums go through atomics, not through the ring of round sums)
-  if (a.dbg_no_ext) mv_pass<G, S, H, MV_LIST, false>(a, sm, phase_bits, pol_stream, false);
-  else mv_pass<G, S, H, MV_LIST, true>(a, sm, phase_bits, pol_stream, false);
+  mv_pass<G, S, H, MV_LIST, true>(a, sm, phase_bits, pol_stream, false);
 }
 
 // Streaming probe (measurement only): the staging half of k_matvec with the consumer removed -- every warp waits

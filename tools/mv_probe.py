@@ -17,8 +17,7 @@ mesh.set_option("test_no_exchange", 1)
 nr, nnz = A.num_rows(), A.num_nonzeros()
 byts = 12.0 * nnz + 4.0 * (nr + 1) + 16.0 * nr
 print("box", boxes[args.rank], "rows %d nnz %d  make_local %.1f ms" % (nr, nnz, mesh.phase_ms("make_local")))
-for ring, ov in [(r_, o_) for r_ in (1, 0) for o_ in (0, 1, 2, 4)]:
-    mesh.set_option("mv_ring", ring)
+for ring, ov in [(1, o_) for o_ in (0, 1, 2, 4)]:
     mesh.set_option("overlap", ov if ov < 3 else 1)
     mesh.set_option("dbg_no_ext", {3: 1, 4: 2}.get(ov, 0))      # 3: fused without the halo-pointer select, 4: fused without the boundary pass
     for what in ("matvec_op",):
