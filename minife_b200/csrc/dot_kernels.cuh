@@ -247,6 +247,7 @@ __device__ __noinline__ void dot_walk_body(int64_t n, const double *__restrict__
       const int64_t i = (int64_t)ws.sorted[q / DOT_LEAF] * DOT_LEAF + (q % DOT_LEAF);
       ws.replay_prod[q] = i < n ? __dmul_rn(x[i], y[i]) : 0.0;
     }
+    const unsigned long long t_p1 = (w.stats && tid == 0) ? global_ns() : 0ULL;
     for (int g = warp; g <= D; g += NT / 32) {
       const long long lo = g == 0 ? 0 : (long long)ws.sorted[g - 1] + 1, hi = g == D ? nleaves : (long long)ws.sorted[g];
       WalkPiece pc[DOT_GAP_PIECES];
@@ -276,6 +277,7 @@ __device__ __noinline__ void dot_walk_body(int64_t n, const double *__restrict__
       if (lane == 31) ws.gmaps[g] = gm;
     }
     __syncthreads();
+    if (w.stats && tid == 0) { const unsigned long long t = global_ns(); w.stats[11] += t_p1 - t_begin; w.stats[12] += t - t_p1; w.stats[13] = t; }
     if (tid == 0) {
       // The sequential part: [gap 0][dirty leaf 0][gap 1] ... [gap D].  Software-pipelined by hand: the map of the next gap
       // and the 16 products of the next dirty leaf are fetched from shared memory BEFORE the dependent chain of the current
@@ -319,7 +321,8 @@ __device__ __noinline__ void dot_walk_body(int64_t n, const double *__restrict__
     if (w.stats) {
       // diagnostics: [0] dots, [1] sum of dirty leaves, [2] max, [3] whole-vector replays, [4] gaps that took the slow path,
       // [5] total ns in the walk, [6] max ns, [7] dot index of the max; then a ring of (dirty leaves, ns) per dot
-      const unsigned long long dt = global_ns() - t_begin, idx = w.stats[0];
+      const unsigned long long t_now = global_ns(), dt = t_now - t_begin, idx = w.stats[0];
+      if (D <= DOT_MAX_DIRTY) w.stats[14] += t_now - w.stats[13];      // [11] prologue (list, sort, products) [12] gap maps [14] sequential part, ns
       w.stats[0] = idx + 1; w.stats[1] += (unsigned long long)D; if ((unsigned long long)D > w.stats[2]) w.stats[2] = D;
       if (D > DOT_MAX_DIRTY) w.stats[3] += 1;
       w.stats[4] += (unsigned long long)slow_gaps; w.stats[5] += dt;

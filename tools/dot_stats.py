@@ -16,7 +16,7 @@ L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 1)
 it, nr, t = mf.cg_solve(A, None, None, None, args.iters, 2.2e-16)
 L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 0)
 print("nx", n, "iters", it, "dots", int(st[0]), "dirty sum/max", int(st[1]), int(st[2]), "full replays", int(st[3]), "slow gaps", int(st[4]),
-      "walk ms total/max", st[5] / 1e6, st[6] / 1e6, "slowest dot #", int(st[7]), "slow pieces", int(st[8]), "cg DOT_s", t[1], "TOTAL_s", t[4])
+      "walk ms total/max", st[5] / 1e6, st[6] / 1e6, "phases us/dot: prologue %.1f gaps %.1f serial %.1f" % (st[11] / max(st[0], 1) / 1e3, st[12] / max(st[0], 1) / 1e3, st[14] / max(st[0], 1) / 1e3), "slowest dot #", int(st[7]), "slow pieces", int(st[8]), "cg DOT_s", t[1], "TOTAL_s", t[4])
 for i in range(min(int(st[0]), 40)):
     w = int(st[16 + 2 * i])
     try:
