@@ -154,7 +154,6 @@ struct mfe_ctx {
   int mv_cfg = 0;                // SpMV configuration (see matvec_configs): 16 warps x 1 stage, 2 gather batches per row
   int tr = MV_TILE_ROWS;         // rows per SpMV tile
   int dot_maps_warps = 0;        // warps per CTA of k_dot_maps: 0 = default (32 for x.x, 24 for x.y), else 16, 24 or 32
-  int dot_maps_version = 0;      // 0: piece-level fast path (round 2), 1: the round-1 kernel (A/B measurements)
 
   // comm
   ncclComm_t_ comm = nullptr;
@@ -974,8 +973,6 @@ static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const dou
   const size_t smem = DotMapsCfg<SAME, NW>::SMEM_BYTES;
   auto kern = k_dot_maps<SAME, NW>;
   if (set_smem_attr_once(kern, attr_set, c->device, smem)) return 1;
-  static bool attr_set_v1[64] = { false };
-  if (c->dot_maps_version == 1 && set_smem_attr_once(k_dot_maps_v1<SAME, NW>, attr_set_v1, c->device, smem)) return 1;
   const int64_t npieces = (n + DOT_PIECE - 1) / DOT_PIECE;
   if (npieces == 0) return 0;
   // one persistent CTA per SM owning a contiguous range of pieces (more CTAs only when a range would overflow the table)
@@ -983,8 +980,7 @@ static int launch_dot_maps_cfg(mfe_ctx *c, int64_t n, const double *x, const dou
   grid = std::max<int64_t>(grid, (npieces + DOT_MAPS_MAX_PP - 1) / DOT_MAPS_MAX_PP);
   const int PP = (int)((npieces + grid - 1) / grid);
   grid = (npieces + PP - 1) / PP;
-  if (c->dot_maps_version == 1) CK(launch_cg(c, k_dot_maps_v1<SAME, NW>, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
-  else CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
+  CK(launch_cg(c, kern, dim3((unsigned)grid), dim3(32 * NW), smem, n, x, y, w, (int)npieces, PP, gate, k));
   return 0;
 }
 
@@ -994,7 +990,7 @@ static int launch_dot_maps(mfe_ctx *c, int64_t n, const double *x, const double 
   // x.x dots stage 4 KB per warp: 32 warps (64 registers) fit and are ~15 us faster per dot than 24 (the kernel is bound by
   // dependent-issue latency, so warps count); x.y dots stage 8 KB per warp: 24
   int nw = c->dot_maps_warps ? c->dot_maps_warps : (x == y ? 32 : 24);
-  if (nw == 32 && (x != y || c->dot_maps_version == 1)) nw = 24;
+  if (nw == 32 && x != y) nw = 24;
   if (x == y) return nw == 32 ? launch_dot_maps_cfg<true, 32>(c, n, x, y, w, gate, k) : nw == 24 ? launch_dot_maps_cfg<true, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<true, 16>(c, n, x, y, w, gate, k);
   return nw == 24 ? launch_dot_maps_cfg<false, 24>(c, n, x, y, w, gate, k) : launch_dot_maps_cfg<false, 16>(c, n, x, y, w, gate, k);
 }
@@ -1389,7 +1385,6 @@ extern "C" int mfe_set_option(mfe_ctx *c, const char *name, int64_t value)
   if (!strcmp(name, "fused")) { c->fused = value != 0; return 0; }
   if (!strcmp(name, "x_overlap")) { c->x_overlap = value != 0; return 0; }
   if (!strcmp(name, "assembly_mode")) { c->assembly_mode = value != 0; return 0; }
-  if (!strcmp(name, "dot_maps_version")) { c->dot_maps_version = value != 0; return 0; }
   if (!strcmp(name, "test_no_exchange")) { c->test_no_exchange = value != 0; return 0; }
   if (!strcmp(name, "dbg_no_ext")) { c->dbg_no_ext = (int)value; return 0; }
   if (!strcmp(name, "mv_ring")) { c->mv_ring = value != 0; return 0; }

@@ -602,193 +602,6 @@ k_dot_maps(int64_t n, const double *__restrict__ x, const double *__restrict__ y
   }
 }
 
-// Round-1 version of the map phase (per-leaf prediction and ordered scans for every piece), kept for A/B measurements
-// (mfe_set_option "dot_maps_version" 1).
-template <bool SAME, int NW>
-__global__ void __launch_bounds__(32 * NW, 1)
-k_dot_maps_v1(int64_t n, const double *__restrict__ x, const double *__restrict__ y, DotWork w, int npieces, int PP, const CgScalars *gate, int k)
-{
-  constexpr int STAGE = DotMapsCfg<SAME, NW>::STAGE_BYTES;
-  constexpr int NT = 32 * NW;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int tid = threadIdx.x, lane = tid & 31, wq = tid >> 5;
-  double *stage = reinterpret_cast<double *>(smem + (size_t)wq * STAGE);
-  uint64_t *bar = reinterpret_cast<uint64_t *>(smem + (size_t)NW * STAGE) + wq;
-  double *table = reinterpret_cast<double *>(smem + (size_t)NW * STAGE + (size_t)NW * 8);
-  double *red = table + (DOT_MAPS_MAX_PP + 1);                  // [2][NW]
-  int *ccnt = reinterpret_cast<int *>(red + 2 * NW);            // arrivals per chunk of this CTA's range
-  const int nchunks = (npieces + DOT_PIECES_PER_CHUNK - 1) / DOT_PIECES_PER_CHUNK;
-  const int p0 = blockIdx.x * PP;
-  const int np = min(PP, npieces - p0);                         // pieces of this CTA
-  if (np <= 0) return;
-
-  auto issue = [&](int piece) {
-    const int64_t b = (int64_t)piece * DOT_PIECE;
-    const int64_t cntp = n - b < DOT_PIECE ? n - b : DOT_PIECE;
-    const uint32_t bytes = (uint32_t)(((cntp + 1) & ~1LL) * 8);  // multiple of 16; the vectors carry >= 8 doubles of slack
-    mbar_expect_tx(bar, SAME ? bytes : 2 * bytes);
-    bulk_g2s(stage, x + b, bytes, bar);
-    if (!SAME) bulk_g2s(stage + DOT_PIECE, y + b, bytes, bar);
-  };
-  if (lane == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  for (int i = tid; i < DotMapsCfg<SAME, NW>::MAX_CHUNKS; i += NT) ccnt[i] = 0;
-  __syncthreads();
-  if (cg_gate_closed(gate, k)) return;
-  if (lane == 0 && wq < np) issue(p0 + wq);                     // first piece of every warp is in flight during the prologue
-
-  // ---- prologue: predicted running sum at the start of every piece of this CTA ----
-  {
-    const int c0 = p0 / DOT_PIECES_PER_CHUNK;
-    double part = 0.0;
-    for (int i = tid; i < c0; i += NT) part += w.chunk_sums[i];
-    if (tid < p0 - c0 * DOT_PIECES_PER_CHUNK) part += w.piece_sums[c0 * DOT_PIECES_PER_CHUNK + tid];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    // runs of R consecutive pieces per thread
-    const int R = (np + NT - 1) / NT, j0 = tid * R;
-    double run = 0.0;
-    for (int q = 0; q < R; ++q) if (j0 + q < np) run += w.piece_sums[p0 + j0 + q];
-    double inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    if (lane == 31) red[NW + wq] = inc;
-    if (lane == 0) red[wq] = part;
-    __syncthreads();
-    double B0 = 0.0, woff = 0.0;
-#pragma unroll
-    for (int q = 0; q < NW; ++q) { B0 += red[q]; if (q < wq) woff += red[NW + q]; }
-    double acc = woff + (inc - run);
-    for (int q = 0; q < R; ++q) if (j0 + q < np) { table[j0 + q] = B0 + acc; acc += w.piece_sums[p0 + j0 + q]; }
-    if (tid == NT - 1) table[np] = B0 + acc;
-    __syncthreads();
-  }
-
-  uint32_t parity = 0;
-  for (int j = wq; j < np; j += NW) {
-    const int piece = p0 + j;
-    const int64_t lbeg = (int64_t)piece * DOT_PIECE + lane * DOT_LEAF;
-    const int cnt = (int)(lbeg >= n ? 0 : (n - lbeg < DOT_LEAF ? n - lbeg : DOT_LEAF));
-    mbar_wait(bar, parity);
-    parity ^= 1u;
-    const double *xs = stage + lane * DOT_LEAF, *ys = SAME ? xs : xs + DOT_PIECE;
-    // products rounded once (fl(x*y)) exactly as the serial loop forms them
-    double prod[DOT_LEAF];
-    if (cnt == DOT_LEAF) {
-      // byte address of element i ^ rot of this lane's leaf: the leaf base is 128-byte aligned, so OR = ADD
-      const uint32_t lbase = smem_u32(xs), rotb = (uint32_t)(lane & (DOT_LEAF - 1)) * 8u;
-#pragma unroll
-      for (int i = 0; i < DOT_LEAF; ++i) {
-        const uint32_t a = lbase | ((uint32_t)(i * 8) ^ rotb);
-        const double xv = lds_f64(a);
-        prod[i] = SAME ? __dmul_rn(xv, xv) : __dmul_rn(xv, lds_f64_off<DOT_PIECE * 8>(a));
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < DOT_LEAF; ++i) prod[i] = i < cnt ? __dmul_rn(xs[i], ys[i]) : 0.0;
-    }
-    double ls = 0.0;
-#pragma unroll
-    for (int i = 0; i < DOT_LEAF; ++i) ls += prod[i];
-    double inc = ls;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
-    const double pre = table[j] + (inc - ls);
-    const int hyp = dot_hyp_of(pre);
-    int hyp_end = __shfl_down_sync(0xffffffffu, hyp, 1);       // predicted binade at the start of the next leaf
-    if (lane == 31) hyp_end = dot_hyp_of(table[j + 1]);
-
-    bool simple = false, risky = false;
-    double sa = 0.0, slo = 0.0, shi = 0.0;
-    DotMap m = dot_identity();
-    if (cnt == DOT_LEAF && hyp >= 0 && hyp != HYP_ZERO) {
-      simple = dot_leaf16_simple(prod, hyp, pre, sa, slo, shi);
-      if (!simple) {                                           // exact tie / near a binade boundary: ordered, exact bounds
-#pragma unroll
-        for (int i = 0; i < DOT_LEAF; ++i) prod[i] = SAME ? __dmul_rn(xs[i], xs[i]) : __dmul_rn(xs[i], ys[i]);
-        m = dot_leaf_map16_fp(prod, hyp);
-        risky = dot_leaf_risky(m, hyp, pre);
-      }
-    } else if (cnt == DOT_LEAF) {
-      m = dot_leaf_map16(prod, hyp, pre);                      // hyp < 0, or the running sum is exactly +0.0 (order independent)
-    } else if (cnt > 0) {
-      m = dot_leaf_map(x, y, lbeg, lbeg + cnt, hyp);           // ragged last leaf of the vector
-    }
-    const bool dirty = cnt > 0 && ((!simple && m.hyp == HYP_INVALID) || hyp != hyp_end || risky);
-    const bool piece_dirty = __any_sync(0xffffffffu, dirty);
-    __syncwarp();
-    if (lane == 0 && j + NW < np) issue(piece + NW);           // the stage is free: next piece in flight while we publish
-
-    // ordered collapse of the 32 leaves onto lane 31
-    const int hyp0 = __shfl_sync(0xffffffffu, hyp, 0);
-    const bool all_simple = __all_sync(0xffffffffu, simple && hyp == hyp0);
-    DotMap wm;
-    if (all_simple) {
-      // simple maps compose in floating point: a = fa + ga, lo = min(flo, fa + glo), hi = max(fhi, fa + ghi); every
-      // value is an exact integer while below 2^53, and a map that ever exceeds 2^52 is unusable (checked below)
-      double ca = sa, clo = slo, chi = shi;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const double fa = __shfl_up_sync(0xffffffffu, ca, o), flo = __shfl_up_sync(0xffffffffu, clo, o), fhi = __shfl_up_sync(0xffffffffu, chi, o);
-        if (lane >= o) {
-          const double nlo = fa + clo, nhi = fa + chi;
-          clo = flo < nlo ? flo : nlo;
-          chi = fhi > nhi ? fhi : nhi;
-          ca = fa + ca;
-        }
-      }
-      if (clo > -4503599627370496.0 && chi < 4503599627370496.0) {
-        wm.a0 = (long long)ca; wm.a1 = wm.a0; wm.lo = (long long)clo; wm.hi = (long long)chi; wm.hyp = hyp0; wm.pad = 0;
-      } else wm = dot_invalid();
-    } else {
-      if (simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
-      wm = warp_compose(m, lane);
-    }
-    if (piece_dirty) {
-      // keep the 32 leaf maps so that the walker can stitch around the dirty leaves of this piece
-      if (all_simple) { m.a0 = (long long)sa; m.a1 = m.a0; m.lo = (long long)slo; m.hi = (long long)shi; m.hyp = hyp; m.pad = 0; }
-      w.leaf_maps[(int64_t)piece * 32 + lane] = m;
-      if (dirty) {
-        const int slot = atomicAdd(w.dirty_count, 1);
-        if (slot < DOT_MAX_DIRTY) w.dirty_list[slot] = piece * 32 + lane;
-      }
-    }
-    // publish the piece map.  The pieces of a chunk belong to this CTA (except at the two ends of its range), so
-    // arrivals are counted in shared memory with a CTA-scope fence; only the warp that completes a chunk pays the
-    // device-scope fence + ticket of the chunk level.
-    const int c = piece / DOT_PIECES_PER_CHUNK;
-    const int cfirst = c * DOT_PIECES_PER_CHUNK;
-    const int nin = min(DOT_PIECES_PER_CHUNK, npieces - cfirst);                         // pieces the chunk has
-    const int mine = min(p0 + np, cfirst + nin) - max(p0, cfirst);                       // ... of which in this CTA's range
-    int last = 0;
-    if (lane == 31) {
-      wm.pad = piece_dirty ? 1 : 0;
-      w.warp_maps[piece] = wm;
-      __threadfence_block();
-      last = atomicAdd(&ccnt[c - p0 / DOT_PIECES_PER_CHUNK], 1) == mine - 1;
-      if (last && mine != nin) {                     // chunk shared with a neighbouring CTA: device-wide ticket
-        __threadfence();
-        last = atomicAdd(&w.chunk_cnt[c], mine) + mine == nin;
-        if (last) w.chunk_cnt[c] = 0;
-      }
-    }
-    last = __shfl_sync(0xffffffffu, last, 31);
-    if (last) {
-      __threadfence();
-      // the (up to) 8 piece maps sit on lanes 24..31; three ordered steps leave their composition on lane 31
-      DotMap cm = dot_identity();
-      const int q = lane - (32 - DOT_PIECES_PER_CHUNK);
-      if (q >= 0 && q < nin) { cm = load_map_cg(w.warp_maps + cfirst + q); cm.pad = 0; }
-      cm = warp_compose<DOT_PIECES_PER_CHUNK>(cm, lane);
-      if (lane == 31) cm.pad = 1;
-      dot_publish_chunk_map(w, cm, lane, c, nchunks);
-    }
-  }
-}
-
-
 // the literal serial loop on one device thread (MFE_DOT_SERIAL; validation of the exact dot)
 __global__ void k_dot_serial(int64_t n, const double *__restrict__ x, const double *__restrict__ y, double *result, CgScalars *sc,
                              int epi, int k, double *normr_hist, double *rtrans_hist, double *pap_hist, double *alpha_hist,

@@ -10,7 +10,7 @@ n = args.nx
 g = mf.Box([0, n, 0, n, 0, n]); mesh = mf.simple_mesh_description(g, g)
 A = mf.CSRMatrix(); mf.generate_matrix_structure(mesh, A); mf.assemble_FE_data(mesh, A, None)
 mf.impose_dirichlet(0.0, A, None, bc_rows=0); mf.impose_dirichlet(1.0, A, None, bc_rows=1); mf.make_local_matrix(A)
-mesh.set_option('dot_maps_warps', args.warps); mesh.set_option('dot_maps_version', args.version); mesh.set_option('x_overlap', 0)
+mesh.set_option('dot_maps_warps', args.warps); mesh.set_option('x_overlap', 0)
 L = mf.lib(); st = np.zeros(16 + 1024, np.uint64)
 L.mfe_dot_stats(mesh._h, st.ctypes.data_as(C.c_void_p), len(st), 1)
 it, nr, t = mf.cg_solve(A, None, None, None, args.iters, 2.2e-16)
