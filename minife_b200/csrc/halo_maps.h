@@ -10,6 +10,10 @@
 #include <vector>
 #include "mesh.h"
 
+#ifndef MFE_HALO_THREADS
+#define MFE_HALO_THREADS 1   /* helper threads for the neighbours' shells (measured: more than one loses to allocator contention) */
+#endif
+
 namespace mfe {
 
 struct ExtEntry { int64_t first; int grow; int owner; };
@@ -72,20 +76,26 @@ inline int owner_of_row(const MeshDesc &gm, int grow)
     if (gm.boxes[p].nrows > 0 && gm.boxes[p].first_row <= grow) { owner = p; break; }     // make_local_matrix.hpp:135-143
   return owner;
 }
+inline int64_t shell_bound(const RankBox &B)
+{
+  const int64_t lx = B.nb[1] - B.nb[0], ly = B.nb[3] - B.nb[2], lz = B.nb[5] - B.nb[4];
+  return (lx + 2) * (ly + 2) * (lz + 2) - lx * ly * lz;
+}
 
 // externals of rank p in the reference's first-encounter order
 inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
 {
   std::vector<uint64_t> keys;
-  const RankBox &B = gm.boxes[p];
-  keys.reserve((size_t)2 * ((int64_t)(B.nb[1] - B.nb[0] + 2) * (B.nb[3] - B.nb[2] + 2) + (int64_t)(B.nb[1] - B.nb[0] + 2) * (B.nb[5] - B.nb[4] + 2) +
-                            (int64_t)(B.nb[3] - B.nb[2] + 2) * (B.nb[5] - B.nb[4] + 2)));
+  keys.reserve((size_t)shell_bound(gm.boxes[p]));
   for_each_external(gm, p, [&](int64_t first, int grow, int) { keys.push_back(ext_key(first, grow)); });
   std::sort(keys.begin(), keys.end());
   out.resize(keys.size());
+  int last = 0;                         // consecutive externals mostly share their owner
   for (size_t i = 0; i < keys.size(); ++i) {
     const int grow = (int)(uint32_t)(keys[i] & 0xffffffffULL);
-    out[i] = ExtEntry{ (int64_t)(keys[i] >> 32), grow, owner_of_row(gm, grow) };
+    const RankBox &b = gm.boxes[last];
+    if (!(b.nrows > 0 && grow >= b.first_row && grow < b.first_row + b.nrows)) last = owner_of_row(gm, grow);
+    out[i] = ExtEntry{ (int64_t)(keys[i] >> 32), grow, last };
   }
 }
 
@@ -97,6 +107,7 @@ inline void externals_of(const MeshDesc &gm, int p, std::vector<ExtEntry> &out)
 inline void peer_wants_from(const MeshDesc &gm, int p, int me, std::vector<ExtEntry> &mine, int &dst_offset)
 {
   std::vector<uint64_t> keys;
+  keys.reserve((size_t)shell_bound(gm.boxes[p]) / 2 + 64);
   std::vector<int> cnt(gm.nranks, 0);
   std::vector<uint64_t> firstkey(gm.nranks, ~0ULL);
   for_each_external(gm, p, [&](int64_t first, int grow, int owner) {
@@ -118,11 +129,12 @@ inline void peer_wants_from(const MeshDesc &gm, int p, int me, std::vector<ExtEn
 inline void group_externals(const std::vector<ExtEntry> &ext, std::vector<int> &owners, std::vector<std::vector<int>> &groups)
 {
   owners.clear(); groups.clear();
+  std::vector<int> slot;                 // owner rank -> group index (or -1)
   for (size_t i = 0; i < ext.size(); ++i) {
-    size_t g = 0;
-    for (; g < owners.size(); ++g) if (owners[g] == ext[i].owner) break;
-    if (g == owners.size()) { owners.push_back(ext[i].owner); groups.emplace_back(); }
-    groups[g].push_back((int)i);
+    const int o = ext[i].owner;
+    if (o >= (int)slot.size()) slot.resize(o + 1, -1);
+    if (slot[o] < 0) { slot[o] = (int)owners.size(); owners.push_back(o); groups.emplace_back(); groups.back().reserve(ext.size() / 4 + 16); }
+    groups[slot[o]].push_back((int)i);
   }
 }
 
@@ -132,6 +144,28 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
   L = LocalMaps();
   const int rank = gm.rank;
   const int nrows = gm.boxes[rank].nrows, first_row = gm.boxes[rank].first_row;
+  // The ranks whose node box touches my one-node shell are exactly my neighbours (the stencil is symmetric); what each of
+  // them needs from me is one pass over ITS shell (make_local_matrix.hpp:386-429), independent of everything else: those
+  // passes run on a few host threads while this thread orders my own externals.
+  const RankBox &B = gm.boxes[rank];
+  std::vector<int> cand;
+  for (int q = 0; q < gm.nranks; ++q) {
+    const RankBox &Q = gm.boxes[q];
+    if (q == rank || Q.nrows == 0) continue;
+    bool touch = true;
+    for (int a = 0; a < 3; ++a) touch = touch && Q.nb[2 * a] < B.nb[2 * a + 1] + 1 && Q.nb[2 * a + 1] > B.nb[2 * a] - 1;
+    if (touch) cand.push_back(q);
+  }
+  const size_t nc = cand.size();
+  std::vector<std::vector<ExtEntry>> mine(nc);
+  std::vector<int> poff(nc, 0);
+  std::vector<std::thread> pool;
+  {
+    const size_t nthreads = std::min<size_t>(nc, MFE_HALO_THREADS);
+    for (size_t t = 0; t < nthreads; ++t)
+      pool.emplace_back([&, t]() { for (size_t i = t; i < nc; i += nthreads) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]); });
+    if (nthreads == 0) for (size_t i = 0; i < nc; ++i) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]);
+  }
   std::vector<ExtEntry> ext;
   externals_of(gm, rank, ext);
   std::vector<int> owners; std::vector<std::vector<int>> groups;
@@ -145,24 +179,17 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
     L.recv_length.push_back((int)groups[g].size());
     for (int i : groups[g]) L.external_local_index[i] = count++;
   }
-  // what each neighbour needs from me, in ITS external order (make_local_matrix.hpp:386-429)
-  L.send_length.assign(L.neighbors.size(), 0);
-  L.send_dst_offset.assign(L.neighbors.size(), 0);
-  // one pass over each neighbour's shell, independent of each other: a few host threads
+  for (std::thread &th : pool) th.join();
   const size_t nn = L.neighbors.size();
-  std::vector<std::vector<ExtEntry>> mine(nn);
-  std::vector<int> poff(nn, 0);
-  {
-    const size_t nthreads = std::min<size_t>(nn, 8);
-    std::vector<std::thread> pool;
-    for (size_t t = 0; t < nthreads; ++t)
-      pool.emplace_back([&, t]() { for (size_t i = t; i < nn; i += nthreads) peer_wants_from(gm, L.neighbors[i], rank, mine[i], poff[i]); });
-    for (std::thread &th : pool) th.join();
-  }
+  L.send_length.assign(nn, 0);
+  L.send_dst_offset.assign(nn, 0);
   for (size_t i = 0; i < nn; ++i) {
-    L.send_length[i] = (int)mine[i].size();
-    L.send_dst_offset[i] = poff[i];
-    for (const ExtEntry &e : mine[i]) L.elements_to_send.push_back(e.grow - first_row);
+    size_t ci = 0;
+    while (ci < nc && cand[ci] != L.neighbors[i]) ++ci;
+    if (ci == nc) continue;               // cannot happen: a neighbour's box touches my shell
+    L.send_length[i] = (int)mine[ci].size();
+    L.send_dst_offset[i] = poff[ci];
+    for (const ExtEntry &e : mine[ci]) L.elements_to_send.push_back(e.grow - first_row);
   }
   L.num_cols = (int64_t)nrows + n_ext;
 }
