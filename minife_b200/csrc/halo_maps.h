@@ -163,7 +163,7 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
   {
     const size_t nthreads = std::min<size_t>(nc, MFE_HALO_THREADS);
     for (size_t t = 0; t < nthreads; ++t)
-      pool.emplace_back([&, t]() { for (size_t i = t; i < nc; i += nthreads) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]); });
+      pool.emplace_back([&, t, nthreads]() { for (size_t i = t; i < nc; i += nthreads) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]); });     // (nthreads by value: the threads outlive this block)
     if (nthreads == 0) for (size_t i = 0; i < nc; ++i) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]);
   }
   std::vector<ExtEntry> ext;
