@@ -4,7 +4,7 @@ import argparse, ctypes as C, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import minife_b200 as mf
-ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=256); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--fold", type=int, default=1); ap.add_argument("--warps", type=int, default=0); ap.add_argument("--version", type=int, default=0)
+ap = argparse.ArgumentParser(); ap.add_argument("--nx", type=int, default=256); ap.add_argument("--iters", type=int, default=20); ap.add_argument("--warps", type=int, default=0)
 args = ap.parse_args()
 n = args.nx
 g = mf.Box([0, n, 0, n, 0, n]); mesh = mf.simple_mesh_description(g, g)

@@ -1,3 +1,6 @@
+"""tools/mv_prof_case.py -- the case ncu was pointed at when the fused SpMV was 35 % slow: rank 0 of a
+2-rank 400^3 run on one GPU (halo supplied by the caller), fused kernel (overlap 1) then the two-launch form (overlap 2).
+    ncu --set full --clock-control none -k regex:k_matvec -c 6 -o prof python tools/mv_prof_case.py"""
 import os, sys
 sys.path.insert(0, "/root/repo")
 import minife_b200 as mf
