@@ -141,6 +141,54 @@ void hs_assemble(void *p, int planes)
   }
 }
 
+// k_assemble_fused thread by thread: columns of BX x BY nodes marched through the node planes with a two-plane ring of
+// element matrices (slot = element plane & 1), elements from the per-axis Jacobian tables, rows gathered out of the ring
+void hs_assemble_ring(void *p, int BX, int BY)
+{
+  Harness *h = (Harness *)p; const MeshDesc &m = h->m;
+  double grad[192], psi[64];
+  hex8_tables(grad, psi);
+  const int nmax = std::max(m.nx, std::max(m.ny, m.nz));
+  std::vector<double> tab((size_t)3 * nmax * 24);
+  const int n[3] = { m.nx, m.ny, m.nz };
+  for (int axis = 0; axis < 3; ++axis)
+    for (int e = 0; e < n[axis]; ++e) {
+      const double c0 = (double)e / (double)n[axis], hh = 1.0 / (double)n[axis], c1 = c0 + hh;
+      for (int g = 0; g < 8; ++g) hex8_jacobian_column(grad, g, axis, c0, c1, &tab[((size_t)axis * nmax + e) * 24 + 3 * g]);
+    }
+  const int WX = BX + 1, WY = BY + 1, NE = WX * WY;
+  std::vector<double> KF((size_t)2 * 44 * NE);
+  for (int by0 = m.nb[2]; by0 < m.nb[3]; by0 += BY)
+    for (int bx0 = m.nb[0]; bx0 < m.nb[1]; bx0 += BX) {
+      const int wx0 = bx0 - 1, wy0 = by0 - 1;
+      auto element_plane = [&](int ez) {
+        if (ez < 0 || ez >= m.nz) return;
+        for (int t = 0; t < NE; ++t) {
+          const int ex = wx0 + t % WX, ey = wy0 + t / WX;
+          if (ex < 0 || ey < 0 || ex >= m.nx || ey >= m.ny || ex >= m.nb[1] || ey >= m.nb[3]) continue;
+          double K[36], f[8];
+          hex8_element_tables(grad, psi, &tab[((size_t)0 * nmax + ex) * 24], &tab[((size_t)1 * nmax + ey) * 24], &tab[((size_t)2 * nmax + ez) * 24], K, f);
+          double *E = &KF[(size_t)((ez & 1) * 44) * NE + t];
+          for (int k = 0; k < 36; ++k) E[(size_t)k * NE] = K[k];
+          for (int k = 0; k < 8; ++k) E[(size_t)(36 + k) * NE] = f[k];
+        }
+      };
+      element_plane(m.nb[4] - 1);
+      for (int iz = m.nb[4]; iz < m.nb[5]; ++iz) {
+        element_plane(iz);
+        for (int t = 0; t < BX * BY; ++t) {
+          const int ix = bx0 + t % BX, iy = by0 + t / BX;
+          if (ix >= m.nb[1] || iy >= m.nb[3]) continue;
+          double acc[27], bsum;
+          gather_row_ring(m, KF.data(), wx0, wy0, WX, NE, ix, iy, iz, acc, bsum);
+          const int64_t lr = (int64_t)(ix - m.nb[0]) + (int64_t)m.lnx * ((iy - m.nb[2]) + (int64_t)m.lny * (iz - m.nb[4]));
+          h->b[lr] = bsum;
+          store_row(m, ix, iy, iz, h->roff[lr], acc, h->coefs.data());
+        }
+      }
+    }
+}
+
 void hs_dirichlet(void *p, int which, double val)
 {
   Harness *h = (Harness *)p; const MeshDesc &m = h->m;

@@ -26,7 +26,7 @@ def H(harness):
     h.hs_create.restype = C.c_void_p; h.hs_create.argtypes = [C.c_int] * 5
     for f in ("hs_destroy", "hs_structure", "hs_make_local"):
         getattr(h, f).argtypes = [C.c_void_p]
-    h.hs_assemble.argtypes = [C.c_void_p, C.c_int]; h.hs_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    h.hs_assemble.argtypes = [C.c_void_p, C.c_int]; h.hs_assemble_ring.argtypes = [C.c_void_p, C.c_int, C.c_int]; h.hs_dirichlet.argtypes = [C.c_void_p, C.c_int, C.c_double]
     for f in ("hs_nrows", "hs_nnz", "hs_num_cols"):
         getattr(h, f).restype = C.c_longlong; getattr(h, f).argtypes = [C.c_void_p]
     h.hs_get_csr.argtypes = [C.c_void_p] * 6
@@ -100,6 +100,10 @@ def test_structure_assembly_dirichlet_maps(H, oracle_built, n, npr, planes):
             assert np.array_equal(rows, R[0]) and np.array_equal(ro, R[1]) and np.array_equal(cols, R[2]), (r, "structure")
         o.assemble_FE_data()
         for r, h in enumerate(hs):
+            # the fused kernel's formulation first (two-plane ring, Jacobian tables; small and odd column sizes so that the
+            # seams between columns and the clipped windows are exercised), then the slab + gather form overwrites it
+            H.hs_assemble_ring(h, 3 + planes % 3, 2 + planes % 4); rows, ro, cols, co, b = get(H, h)
+            assert beq(co, o.csr(r)[3]) and beq(b, o.b(r)), (r, "fused-ring assembly")
             H.hs_assemble(h, planes); rows, ro, cols, co, b = get(H, h)
             assert beq(co, o.csr(r)[3]) and beq(b, o.b(r)), (r, "assembly")
         for w, val in ((0, 0.0), (1, 1.0)):
