@@ -6,6 +6,7 @@
 // The peers' lists (-> elements_to_send) follow from the same rule applied to the peer's box.
 #pragma once
 #include <algorithm>
+#include <system_error>
 #include <thread>
 #include <vector>
 #include "mesh.h"
@@ -159,11 +160,19 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
   const size_t nc = cand.size();
   std::vector<std::vector<ExtEntry>> mine(nc);
   std::vector<int> poff(nc, 0);
-  std::vector<std::thread> pool;
+  struct Pool {                          // joins on every way out of this function (an exception below must not reach ~thread)
+    std::vector<std::thread> th;
+    void join() { for (std::thread &t : th) if (t.joinable()) t.join(); }
+    ~Pool() { join(); }
+  } pool;
   {
-    const size_t nthreads = std::min<size_t>(nc, MFE_HALO_THREADS);
-    for (size_t t = 0; t < nthreads; ++t)
-      pool.emplace_back([&, t, nthreads]() { for (size_t i = t; i < nc; i += nthreads) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]); });     // (nthreads by value: the threads outlive this block)
+    size_t nthreads = std::min<size_t>(nc, MFE_HALO_THREADS);
+    try {
+      for (size_t t = 0; t < nthreads; ++t)
+        pool.th.emplace_back([&, t, nthreads]() { for (size_t i = t; i < nc; i += nthreads) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]); });     // (nthreads by value: the threads outlive this block)
+    } catch (const std::system_error &) {  // no thread to be had: do the passes here
+      pool.join(); pool.th.clear(); nthreads = 0;
+    }
     if (nthreads == 0) for (size_t i = 0; i < nc; ++i) peer_wants_from(gm, cand[i], rank, mine[i], poff[i]);
   }
   std::vector<ExtEntry> ext;
@@ -179,7 +188,7 @@ inline void compute_local_maps(const MeshDesc &gm, LocalMaps &L)
     L.recv_length.push_back((int)groups[g].size());
     for (int i : groups[g]) L.external_local_index[i] = count++;
   }
-  for (std::thread &th : pool) th.join();
+  pool.join();
   const size_t nn = L.neighbors.size();
   L.send_length.assign(nn, 0);
   L.send_dst_offset.assign(nn, 0);
