@@ -10,6 +10,7 @@
 #include <limits>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/minife_b200.h"
@@ -739,26 +740,21 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   hm.boxes = c->boxes.data();
   LocalMaps L;
   compute_local_maps(hm, L);
-  c->external_index = L.external_index; c->external_local_index = L.external_local_index;
-  c->elements_to_send = L.elements_to_send; c->neighbors = L.neighbors;
-  c->recv_length = L.recv_length; c->send_length = L.send_length;
-  c->send_dst_offset = L.send_dst_offset;
+  c->external_index = std::move(L.external_index); c->external_local_index = std::move(L.external_local_index);
+  c->elements_to_send = std::move(L.elements_to_send); c->neighbors = std::move(L.neighbors);
+  c->recv_length = std::move(L.recv_length); c->send_length = std::move(L.send_length);
+  c->send_dst_offset = std::move(L.send_dst_offset);
   c->num_cols = L.num_cols;
   // the peer kernels take the neighbour tables by value (PEER_MAX_NEIGHBORS entries): more neighbours than that
   // (unaligned boxes at np >= 28, add_imbalance) go over NCCL, which has no such limit
   c->peer_fits_local = c->neighbors.size() <= PEER_MAX_NEIGHBORS;
   if (peer_agree(c)) return 1;
   const int n_ext = (int)c->external_index.size();
-  // device: rewrite the columns (owned: col - start_row; external: external_local_index)
-  std::vector<std::pair<int, int>> srt(n_ext);
-  for (int i = 0; i < n_ext; ++i) srt[i] = { c->external_index[i], c->external_local_index[i] };
-  std::sort(srt.begin(), srt.end());
-  std::vector<int> sg(n_ext + 1), slc(n_ext + 1);
-  for (int i = 0; i < n_ext; ++i) { sg[i] = srt[i].first; slc[i] = srt[i].second; }
+  // device: rewrite the columns (owned: col - start_row; external: external_local_index, looked up by global row)
   int *d_sg = nullptr, *d_sl = nullptr;
   if (dev_alloc(&d_sg, n_ext + 1) || dev_alloc(&d_sl, n_ext + 1)) return 1;
-  CK(cudaMemcpyAsync(d_sg, sg.data(), sizeof(int) * (n_ext + 1), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_sl, slc.data(), sizeof(int) * (n_ext + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_sg, L.sorted_global.data(), sizeof(int) * n_ext, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(d_sl, L.sorted_local.data(), sizeof(int) * n_ext, cudaMemcpyHostToDevice, c->stream));
   const int start_row = c->m.first_row, stop_row = c->m.first_row + (int)c->nrows - 1;
   k_localize_cols<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_cols, c->nnz, start_row, stop_row, d_sg, d_sl, n_ext);
   c->launches++;

@@ -205,16 +205,14 @@ void hs_make_local(void *p)
   Harness *h = (Harness *)p; const MeshDesc &m = h->m;
   if (m.nranks == 1) { h->maps = LocalMaps(); h->maps.num_cols = m.nrows; return; }
   compute_local_maps(m, h->maps);
-  const int n_ext = (int)h->maps.external_index.size();
-  std::vector<std::pair<int, int>> srt(n_ext);
-  for (int i = 0; i < n_ext; ++i) srt[i] = { h->maps.external_index[i], h->maps.external_local_index[i] };
-  std::sort(srt.begin(), srt.end());
+  // the lookup k_localize_cols does: binary search of the global row in sorted_global
+  const std::vector<int> &sg = h->maps.sorted_global, &sl = h->maps.sorted_local;
   const int start = m.first_row, stop = m.first_row + m.nrows - 1;
   for (size_t i = 0; i < h->cols.size(); ++i) {
     const int c = h->cols[i];
     if (c >= start && c <= stop) { h->cols[i] = c - start; continue; }
-    auto it = std::lower_bound(srt.begin(), srt.end(), std::make_pair(c, -1));
-    h->cols[i] = (it != srt.end() && it->first == c) ? it->second : -1;
+    auto it = std::lower_bound(sg.begin(), sg.end(), c);
+    h->cols[i] = (it != sg.end() && *it == c) ? sl[it - sg.begin()] : -1;
   }
 }
 
@@ -238,6 +236,8 @@ long long hs_get_map(void *p, const char *name, int *out)
   else if (!strcmp(name, "recv_length")) v = &h->maps.recv_length;
   else if (!strcmp(name, "send_length")) v = &h->maps.send_length;
   else if (!strcmp(name, "send_dst_offset")) v = &h->maps.send_dst_offset;
+  else if (!strcmp(name, "sorted_global")) v = &h->maps.sorted_global;
+  else if (!strcmp(name, "sorted_local")) v = &h->maps.sorted_local;
   else return -1;
   if (out && !v->empty()) memcpy(out, v->data(), v->size() * sizeof(int));
   return (long long)v->size();

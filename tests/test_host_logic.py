@@ -125,6 +125,46 @@ def test_structure_assembly_dirichlet_maps(H, oracle_built, n, npr, planes):
             H.hs_destroy(h)
 
 
+def _big_goldens():
+    import glob, os
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return sorted(os.path.basename(f) for f in glob.glob(os.path.join(d, "big_*.npz")) if "_np1." not in f)
+
+
+@pytest.mark.parametrize("name", _big_goldens())
+def test_index_maps_at_full_size_equal_the_reference_record(name, H):
+    """make_local_matrix's index maps (halo_maps.h: enumerated in encounter order, no sort) at the sizes of BASELINE's
+    multi-rank configurations, on every rank, against the record of the UNMODIFIED reference at that np
+    (tests/golden/make_big_golden.py: lengths and CRC-32 of external_index / external_local_index / elements_to_send,
+    neighbors, recv_length, send_length, num_cols).  Host logic only: no matrix is built."""
+    import os, zlib
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    n, npr = tuple(int(v) for v in g["n"]), int(g["np"])
+    crc = lambda a: np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
+    for r in range(npr):
+        h = H.hs_create(n[0], n[1], n[2], npr, r)
+        try:
+            assert H.hs_nrows(h) == int(g["sizes_%d" % r][0])
+            H.hs_make_local(h)
+            m = {}
+            for k in MAPS + ("sorted_global", "sorted_local"):
+                cnt = H.hs_get_map(h, k.encode(), None); a = np.zeros(cnt, np.int32)
+                if cnt:
+                    H.hs_get_map(h, k.encode(), P(a))
+                m[k] = a
+            assert H.hs_num_cols(h) == int(g["num_cols_%d" % r]), (r, "num_cols")
+            for k in ("neighbors", "recv_length", "send_length"):
+                assert np.array_equal(m[k], g["%s_%d" % (k, r)]), (r, k)
+            for k in ("external_index", "external_local_index", "elements_to_send"):
+                assert len(m[k]) == int(g["len_%s_%d" % (k, r)]) and crc(m[k]) == g["crc_%s_%d" % (k, r)], (r, k)
+            # the column lookup table: the same pairs by ascending global row
+            order = np.argsort(m["external_index"], kind="stable")
+            assert np.array_equal(m["sorted_global"], m["external_index"][order]), (r, "sorted_global")
+            assert np.array_equal(m["sorted_local"], m["external_local_index"][order]), (r, "sorted_local")
+        finally:
+            H.hs_destroy(h)
+
+
 def _dot_cases():
     rng = np.random.default_rng(11)
     for n in (0, 1, 15, 16, 17, 255, 4095, 4096, 4097, 100000, 1234567):
