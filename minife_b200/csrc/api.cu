@@ -753,8 +753,10 @@ extern "C" int mfe_make_local_matrix(mfe_ctx *c, int64_t *num_cols)
   // device: rewrite the columns (owned: col - start_row; external: external_local_index, looked up by global row)
   int *d_sg = nullptr, *d_sl = nullptr;
   if (dev_alloc(&d_sg, n_ext + 1) || dev_alloc(&d_sl, n_ext + 1)) return 1;
-  CK(cudaMemcpyAsync(d_sg, L.sorted_global.data(), sizeof(int) * n_ext, cudaMemcpyHostToDevice, c->stream));
-  CK(cudaMemcpyAsync(d_sl, L.sorted_local.data(), sizeof(int) * n_ext, cudaMemcpyHostToDevice, c->stream));
+  if (n_ext > 0) {
+    CK(cudaMemcpyAsync(d_sg, L.sorted_global.data(), sizeof(int) * n_ext, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_sl, L.sorted_local.data(), sizeof(int) * n_ext, cudaMemcpyHostToDevice, c->stream));
+  }
   const int start_row = c->m.first_row, stop_row = c->m.first_row + (int)c->nrows - 1;
   k_localize_cols<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_cols, c->nnz, start_row, stop_row, d_sg, d_sl, n_ext);
   c->launches++;
