@@ -56,3 +56,44 @@ def test_400_cubed_equals_the_reference_record(product_lib):
         assert crc(x.coefs) == g["crc_x_0"], "solution"
     finally:
         mesh.close()
+
+
+def test_512_cubed_size_independent_properties(product_lib):
+    """BASELINE configs[4] (512^3, 135 M rows, 57 GB on the device): no reference record exists at this size (the reference
+    needs more host memory than the authoring container has), so the checks are the size-independent ones: closed-form
+    row / nonzero counts, row lengths between 8 and 27, a 200-iteration solve with a finite, decreasing residual, and the
+    order-reproducing dot of the solution with itself equal -- bit for bit -- to the literal serial loop on the device
+    (dot mode 1), which is the reference's summation order (ref/src/Vector_functions.hpp:194-226)."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs a 100 GB device")
+    n = 512
+    gbox = mf.Box([0, n, 0, n, 0, n])
+    mesh = mf.simple_mesh_description(gbox, gbox)
+    try:
+        A = mf.CSRMatrix()
+        mf.generate_matrix_structure(mesh, A)
+        N = (n + 1) ** 3
+        assert A.num_rows() == N and A.num_nonzeros() == (3 * (n + 1) - 2) ** 3
+        lens = np.diff(A.row_offsets64)
+        assert lens.min() == 8 and lens.max() == 27 and int(lens.sum()) == A.num_nonzeros()
+        del lens
+        b = mf.Vector(0, N)
+        x = mf.Vector(0, N)
+        mf.assemble_FE_data(mesh, A, b)
+        mf.impose_dirichlet(0.0, A, b, bc_rows=0)
+        mf.impose_dirichlet(1.0, A, b, bc_rows=1)
+        mf.make_local_matrix(A)
+        iters, normr, times, h = mf.cg_solve(A, b, x, mf.matvec_std(), 200, EPS, history=True)
+        assert iters == 200
+        assert len(h["normr"]) == 201 and np.all(np.isfinite(h["normr"])) and 0.0 < h["normr"][200] < h["normr"][0]
+        d_exact = mf.dot(x, x, ctx=mesh)
+        mesh.set_dot_mode(1)
+        try:
+            d_serial = mf.dot(x, x, ctx=mesh)
+        finally:
+            mesh.set_dot_mode(0)
+        assert np.float64(d_exact).view(np.int64) == np.float64(d_serial).view(np.int64), (d_exact, d_serial)
+        assert d_exact > 0.0
+    finally:
+        mesh.close()
