@@ -244,6 +244,11 @@ def golden_for(dims, world):
         fn = os.path.join(g, "history_%d.npz" % dims[0])
         if os.path.exists(fn):
             return fn, np.load(fn)
+    # sizes the reference cannot hold in the authoring container: the record of the oracle (tests/golden/make_oracle_golden.py),
+    # which equals the reference's record bit for bit wherever both exist
+    fn = os.path.join(g, "oracle_%dx%dx%d_np%d.npz" % (dims[0], dims[1], dims[2], world))
+    if os.path.exists(fn):
+        return fn, np.load(fn)
     return None, None
 
 
@@ -295,6 +300,9 @@ def check_parity(mesh, mf, L, dims, rank, world, dist, torch, iters, hist):
         nbad = int(t)
     if nbad:
         raise SystemExit("PARITY FAILURE against %s: %s" % (os.path.basename(fn), "; ".join(bad) or "on another rank"))
+    if os.path.basename(fn).startswith("oracle_"):
+        return ("oracle golden np=%d ok (%s: %d residual norms and the solution CRC on every rank bit-equal to the CPU oracle's record; the reference "
+                "itself does not fit the authoring container at this size, the oracle equals it bit for bit at every size where both run)" % (world, os.path.basename(fn), k + 1))
     return "golden np=%d ok (%s: %d residual norms and the solution CRC on every rank bit-equal to the unmodified reference)" % (world, os.path.basename(fn), k + 1)
 
 

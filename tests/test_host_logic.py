@@ -128,7 +128,7 @@ def test_structure_assembly_dirichlet_maps(H, oracle_built, n, npr, planes):
 def _big_goldens():
     import glob, os
     d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    return sorted(os.path.basename(f) for f in glob.glob(os.path.join(d, "big_*.npz")) if "_np1." not in f)
+    return sorted(os.path.basename(f) for f in glob.glob(os.path.join(d, "big_*.npz")) + glob.glob(os.path.join(d, "oracle_*.npz")) if "_np1." not in f)
 
 
 @pytest.mark.parametrize("name", _big_goldens())
@@ -136,7 +136,8 @@ def test_index_maps_at_full_size_equal_the_reference_record(name, H):
     """make_local_matrix's index maps (halo_maps.h: enumerated in encounter order, no sort) at the sizes of BASELINE's
     multi-rank configurations, on every rank, against the record of the UNMODIFIED reference at that np
     (tests/golden/make_big_golden.py: lengths and CRC-32 of external_index / external_local_index / elements_to_send,
-    neighbors, recv_length, send_length, num_cols).  Host logic only: no matrix is built."""
+    neighbors, recv_length, send_length, num_cols); at 512^3, which the reference cannot hold here, against the record of
+    the oracle (oracle_*.npz, tests/golden/make_oracle_golden.py).  Host logic only: no matrix is built."""
     import os, zlib
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
     n, npr = tuple(int(v) for v in g["n"]), int(g["np"])
