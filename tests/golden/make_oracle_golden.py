@@ -8,9 +8,10 @@ needs 51 GB.  One process simulates all np ranks (serial-order dot per rank, ran
     python tests/golden/make_oracle_golden.py --check 256x256x256:8  # same run, compared with the REFERENCE's own record
                                                                      #    tests/golden/big_256x256x256_np8.npz instead of stored
 
-The file holds the same keys as tests/golden/big_*.npz (make_big_golden.py) except the CRCs of cols / coefs (skipped to
-stay inside the memory of the container): sizes, boxes, CRC-32 of row_offsets, b before / after the Dirichlet
-conditions, x, the index maps, and the four per-iteration histories of the 200-iteration solve.  `source` = "oracle".
+The file holds the same keys as tests/golden/big_*.npz (make_big_golden.py) except the CRCs of row_offsets / cols / coefs
+(copying those arrays out would not fit the memory of the container next to the oracle's own): sizes, boxes, CRC-32 of b
+before / after the Dirichlet conditions and of x, the index maps, and the four per-iteration histories of the
+200-iteration solve.  `source` = "oracle".
 bench.py falls back to such a file when no reference record exists for its configuration and says so in `parity`.
 """
 import os
