@@ -11,11 +11,23 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* Row offsets are `int` as in the reference (MINIFE_LOCAL_ORDINAL=int).  -DMFO_WIDE_OFFSETS makes them 64-bit so that one
+ * rank can hold 512^3 (3.6e9 nonzeros) -- the route SURVEY 0.6 names for the reference itself (MINIFE_LOCAL_ORDINAL=
+ * 'long long').  Only the type of the offsets and of the loop counters that walk the packed arrays changes: column
+ * indices stay int, no arithmetic on values is touched.  tests/golden/make_oracle_golden.py --check pins the wide build to
+ * the reference's own records. */
+#ifdef MFO_WIDE_OFFSETS
+typedef long long mfo_off;
+#else
+typedef int mfo_off;
+#endif
+
 typedef struct {
   int box[6];      /* element box  [x0,x1,y0,y1,z0,z1) */
   int nbox[6];     /* owned-node box */
   int nrows, first_row;
-  int *rows, *row_offsets, *cols;
+  int *rows, *cols;
+  mfo_off *row_offsets;
   double *coefs, *b, *x;
   int *bc[2]; int nbc[2];
   int num_cols, has_local;
@@ -173,13 +185,13 @@ int mfo_generate_matrix_structure(mfo_world *w)
     int nrows = R->nrows, roff = 0, ix, iy, iz, sx, sy, sz;
     long long nnz = 0;
     R->rows = (int *)malloc(sizeof(int) * (nrows + 1));
-    R->row_offsets = (int *)malloc(sizeof(int) * (nrows + 1));
+    R->row_offsets = (mfo_off *)malloc(sizeof(mfo_off) * (nrows + 1));
     R->cols = (int *)malloc(sizeof(int) * ((size_t)nrows * 27 + 1));
     R->coefs = (double *)malloc(sizeof(double) * ((size_t)nrows * 27 + 1));
     for (iz = nb[4]; iz < nb[5]; ++iz) for (iy = nb[2]; iy < nb[3]; ++iy) for (ix = nb[0]; ix < nb[1]; ++ix) {
       int len = 0, *rc = R->cols + nnz, i, j;
       R->rows[roff] = map_id_to_row(w, get_id(w->gnx, w->gny, w->gnz, ix, iy, iz));
-      R->row_offsets[roff++] = (int)nnz;
+      R->row_offsets[roff++] = (mfo_off)nnz;
       for (sz = -1; sz <= 1; ++sz) for (sy = -1; sy <= 1; ++sy) for (sx = -1; sx <= 1; ++sx) {
         int col_id = get_id(w->gnx, w->gny, w->gnz, ix + sx, iy + sy, iz + sz);
         if (col_id >= 0 && col_id < w->global_nrows) { rc[len] = map_id_to_row(w, col_id); R->coefs[nnz + len] = 0; ++len; }
@@ -188,7 +200,7 @@ int mfo_generate_matrix_structure(mfo_world *w)
       for (i = 1; i < len; ++i) { int v = rc[i]; for (j = i; j > 0 && rc[j - 1] > v; --j) rc[j] = rc[j - 1]; rc[j] = v; }
       nnz += len;
     }
-    R->row_offsets[roff] = (int)nnz;
+    R->row_offsets[roff] = (mfo_off)nnz;
     R->b = (double *)calloc(nrows + 1, sizeof(double));   /* Vector ctor zero-fills, Vector.hpp:44-52 */
     R->x = (double *)calloc(nrows + 1, sizeof(double));
     R->num_cols = 0; R->has_local = 0;
@@ -344,8 +356,8 @@ void mfo_element(int nx, int ny, int nz, int elemID, int *ids8, double *c24, dou
 /* ---- ref/src/SparseMatrix_functions.hpp:142-160 sum_into_row (lower_bound in the sorted row) ---- */
 static void sum_into_row(mfo_rank *R, int local_row, int col, double v)
 {
-  int lo = R->row_offsets[local_row], hi = R->row_offsets[local_row + 1], end = hi;
-  while (lo < hi) { int mid = lo + (hi - lo) / 2; if (R->cols[mid] < col) lo = mid + 1; else hi = mid; }
+  mfo_off lo = R->row_offsets[local_row], hi = R->row_offsets[local_row + 1], end = hi;
+  while (lo < hi) { mfo_off mid = lo + (hi - lo) / 2; if (R->cols[mid] < col) lo = mid + 1; else hi = mid; }
   if (lo < end && R->cols[lo] == col) R->coefs[lo] += v;
 }
 
@@ -393,7 +405,7 @@ void mfo_impose_dirichlet(mfo_world *w, int which)
   int p; double val = which == 0 ? 0.0 : 1.0;
   for (p = 0; p < w->np; ++p) {
     mfo_rank *R = &w->r[p];
-    const int *bc = R->bc[which]; int nbc = R->nbc[which], k, i, j;
+    const int *bc = R->bc[which]; int nbc = R->nbc[which], k, i; mfo_off j;
     int first = R->nrows > 0 ? R->rows[0] : 0, last = R->nrows > 0 ? R->rows[R->nrows - 1] : -1;
     for (k = 0; k < nbc; ++k) {
       int row = bc[k];
@@ -427,8 +439,8 @@ void mfo_make_local_matrix(mfo_world *w)
     for (p = 0; p < np; ++p) {
       mfo_rank *R = &w->r[p];
       int start_row = R->nrows > 0 ? R->rows[0] : -1, stop_row = R->nrows > 0 ? R->rows[R->nrows - 1] : -1;
-      int nnz = R->row_offsets[R->nrows], j, i, num_external = 0, count, *eproc, *newproc;
-      R->external_index = (int *)malloc(sizeof(int) * (nnz + 1));
+      mfo_off nnz = R->row_offsets[R->nrows], j; int i, num_external = 0, count, *eproc, *newproc;
+      R->external_index = (int *)malloc(sizeof(int) * ((size_t)nnz + 1));
       memset(ext_slot, 0xff, sizeof(int) * (size_t)w->global_nrows);
       for (j = 0; j < nnz; ++j) {
         int cur = R->cols[j];
@@ -530,7 +542,7 @@ void mfo_exchange_externals(mfo_world *w, double **x)
 /* ---- ref/src/SparseMatrix_functions.hpp:546-578 matvec_std (local part) ------------------------ */
 void mfo_matvec(mfo_world *w, int rank, const double *x, double *y)
 {
-  mfo_rank *R = &w->r[rank]; int row, i; const double beta = 0;
+  mfo_rank *R = &w->r[rank]; int row; mfo_off i; const double beta = 0;
   for (row = 0; row < R->nrows; ++row) {
     double sum = beta * y[row];
     for (i = R->row_offsets[row]; i < R->row_offsets[row + 1]; ++i) sum += R->coefs[i] * x[R->cols[i]];
@@ -550,7 +562,7 @@ void mfo_rearrange_matrix_local_external(mfo_world *w)
   for (p = 0; p < w->np; ++p) {
     mfo_rank *R = &w->r[p]; int row;
     for (row = 0; row < R->nrows; ++row) {
-      int b = R->row_offsets[row], e = R->row_offsets[row + 1], i, j;
+      mfo_off b = R->row_offsets[row], e = R->row_offsets[row + 1], i, j;
       for (i = b + 1; i < e; ++i) {           /* insertion sort of (cols, coefs) by column */
         int c = R->cols[i]; double v = R->coefs[i];
         for (j = i; j > b && R->cols[j - 1] > c; --j) { R->cols[j] = R->cols[j - 1]; R->coefs[j] = R->coefs[j - 1]; }
@@ -661,9 +673,9 @@ long long mfo_first_row(mfo_world *w, int p) { return w->r[p].nrows > 0 ? w->r[p
 void mfo_get_box(mfo_world *w, int p, int *b) { memcpy(b, w->r[p].box, 6 * sizeof(int)); }
 void mfo_get_csr(mfo_world *w, int p, int *rows, int *ro, int *cols, double *coefs)
 {
-  mfo_rank *R = &w->r[p]; size_t nnz = R->row_offsets[R->nrows];
+  mfo_rank *R = &w->r[p]; size_t nnz = (size_t)R->row_offsets[R->nrows]; int i;
   if (rows) memcpy(rows, R->rows, sizeof(int) * R->nrows);
-  if (ro) memcpy(ro, R->row_offsets, sizeof(int) * (R->nrows + 1));
+  if (ro) for (i = 0; i <= R->nrows; ++i) ro[i] = (int)R->row_offsets[i];   /* (truncates in a wide build beyond 2^31) */
   if (cols) memcpy(cols, R->cols, sizeof(int) * nnz);
   if (coefs) memcpy(coefs, R->coefs, sizeof(double) * nnz);
 }

@@ -7,6 +7,9 @@ needs 51 GB.  One process simulates all np ranks (serial-order dot per rank, ran
     python tests/golden/make_oracle_golden.py 512x512x512:8          # -> tests/golden/oracle_512x512x512_np8.npz (~30 min, 1 thread)
     python tests/golden/make_oracle_golden.py --check 256x256x256:8  # same run, compared with the REFERENCE's own record
                                                                      #    tests/golden/big_256x256x256_np8.npz instead of stored
+    python tests/golden/make_oracle_golden.py --wide 512x512x512:1   # one rank, 3.6e9 nonzeros: the oracle built with 64-bit row
+                                                                     #    offsets (oracle/Makefile oracle-wide); --wide --check
+                                                                     #    400x400x400:1 pins that build to the reference's record
 
 The file holds the same keys as tests/golden/big_*.npz (make_big_golden.py) except the CRCs of row_offsets / cols / coefs
 (copying those arrays out would not fit the memory of the container next to the oracle's own): sizes, boxes, CRC-32 of b
@@ -23,6 +26,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
+import oracle_lib  # noqa: E402
 from oracle_lib import Oracle, EPS  # noqa: E402
 
 MAPS = ("external_index", "external_local_index", "elements_to_send", "neighbors", "recv_length", "send_length")
@@ -32,10 +36,31 @@ def crc(a):
     return np.uint32(zlib.crc32(np.ascontiguousarray(a).tobytes()))
 
 
-def oracle_case(n, npr, max_iter=200):
+class WideOracle(Oracle):
+    """oracle/libminife_oracle_wide.so: the same source compiled with -DMFO_WIDE_OFFSETS (64-bit row offsets, `make -C oracle
+    oracle-wide`), for one rank holding 2^31 nonzeros or more (512^3 at np = 1)."""
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            import subprocess
+            subprocess.run(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle"), "oracle-wide"], check=True)
+            Oracle._lib = None                             # let the base class bind its prototypes to the wide library
+            saved = oracle_lib.ORACLE_SO
+            oracle_lib.ORACLE_SO = saved.replace("libminife_oracle.so", "libminife_oracle_wide.so")
+            try:
+                cls._lib = Oracle.lib.__func__(Oracle)
+            finally:
+                oracle_lib.ORACLE_SO = saved
+                Oracle._lib = None
+        return cls._lib
+
+
+def oracle_case(n, npr, max_iter=200, wide=False):
     t0 = time.time()
-    out = dict(n=np.array(n), np=npr, source="oracle")
-    o = Oracle(n[0], n[1], n[2], npr)
+    out = dict(n=np.array(n), np=npr, source="oracle (64-bit row offsets)" if wide else "oracle")
+    o = (WideOracle if wide else Oracle)(n[0], n[1], n[2], npr)
     o.generate_matrix_structure()
     for r in range(npr):
         out["box_%d" % r] = o.box(r)
@@ -70,13 +95,13 @@ def oracle_case(n, npr, max_iter=200):
 
 
 def main():
-    check = "--check" in sys.argv[1:]
+    check, wide = "--check" in sys.argv[1:], "--wide" in sys.argv[1:]
     for spec in [a for a in sys.argv[1:] if not a.startswith("--")]:
         dims, npr = spec.split(":")
         n = tuple(int(v) for v in dims.split("x")); npr = int(npr)
         if check:
             ref = np.load(os.path.join(HERE, "big_%dx%dx%d_np%d.npz" % (n + (npr,))))
-            d = oracle_case(n, npr)
+            d = oracle_case(n, npr, wide=wide)
             bad = []
             for k, v in d.items():
                 if k in ("wall_s", "source"):
@@ -95,7 +120,7 @@ def main():
         if os.path.exists(fn):
             print("have", fn, flush=True)
             continue
-        np.savez_compressed(fn, **oracle_case(n, npr))
+        np.savez_compressed(fn, **oracle_case(n, npr, wide=wide))
         print("wrote", fn, flush=True)
 
 
