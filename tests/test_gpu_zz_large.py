@@ -13,6 +13,7 @@ from oracle_lib import EPS
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "big_400x400x400_np1.npz")
+ORACLE_512 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_512x512x512_np1.npz")
 
 
 def crc(a):
@@ -59,11 +60,13 @@ def test_400_cubed_equals_the_reference_record(product_lib):
 
 
 def test_512_cubed_size_independent_properties(product_lib):
-    """BASELINE configs[4] (512^3, 135 M rows, 57 GB on the device): no reference record exists at this size (the reference
-    needs more host memory than the authoring container has), so the checks are the size-independent ones: closed-form
-    row / nonzero counts, row lengths between 8 and 27, a 200-iteration solve with a finite, decreasing residual, and the
-    order-reproducing dot of the solution with itself equal -- bit for bit -- to the literal serial loop on the device
-    (dot mode 1), which is the reference's summation order (ref/src/Vector_functions.hpp:194-226)."""
+    """BASELINE configs[4] (512^3, 135 M rows, 57 GB on the device).  The reference cannot run at this size in the authoring
+    container (65 GB, and 3.6e9 nonzeros overflow its `int` offsets); the CPU oracle built with 64-bit row offsets can, and
+    its record (tests/golden/oracle_512x512x512_np1.npz) is compared bit for bit: b after assembly and after the Dirichlet
+    conditions, the four per-iteration histories, the solution.  Beside it the size-independent checks: closed-form row /
+    nonzero counts, row lengths between 8 and 27, and the order-reproducing dot of the solution with itself equal -- bit for
+    bit -- to the literal serial loop on the device (dot mode 1), the reference's summation order
+    (ref/src/Vector_functions.hpp:194-226)."""
     import torch
     if torch.cuda.get_device_properties(0).total_memory < 100e9:
         pytest.skip("needs a 100 GB device")
@@ -80,13 +83,26 @@ def test_512_cubed_size_independent_properties(product_lib):
         del lens
         b = mf.Vector(0, N)
         x = mf.Vector(0, N)
+        g = np.load(ORACLE_512) if os.path.exists(ORACLE_512) else None
         mf.assemble_FE_data(mesh, A, b)
+        if g is not None:
+            assert (N, A.num_nonzeros()) == tuple(int(v) for v in g["sizes_0"])
+            assert crc(b.coefs) == g["crc_b_prebc_0"], "b after assembly"
         mf.impose_dirichlet(0.0, A, b, bc_rows=0)
         mf.impose_dirichlet(1.0, A, b, bc_rows=1)
+        if g is not None:
+            assert crc(b.coefs) == g["crc_b_0"], "b after the Dirichlet conditions"
         mf.make_local_matrix(A)
         iters, normr, times, h = mf.cg_solve(A, b, x, mf.matvec_std(), 200, EPS, history=True)
         assert iters == 200
         assert len(h["normr"]) == 201 and np.all(np.isfinite(h["normr"])) and 0.0 < h["normr"][200] < h["normr"][0]
+        if g is not None:
+            # the record of the CPU oracle at this size (64-bit row offsets; tests/golden/make_oracle_golden.py --wide, pinned to
+            # the reference's own 400^3 record): all four histories and the solution, bit for bit
+            for name in ("normr", "rtrans", "pap", "alpha"):
+                lo = 1 if name in ("pap", "alpha") else 0
+                assert np.array_equal(bits(h[name][lo:201]), bits(g[name][lo:201])), "%s history" % name
+            assert crc(x.coefs) == g["crc_x_0"], "solution"
         d_exact = mf.dot(x, x, ctx=mesh)
         mesh.set_dot_mode(1)
         try:
